@@ -1,0 +1,156 @@
+/*
+ * pnp_pds.h — C ABI of the B200-native PnP-PDS hot path (libpnp_pds.so).
+ *
+ * The reference (yodai49/PnP-PDS) is function-level Python with no FFI boundary of its own
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds (ctypes stub in
+ * INTEGRATION.md); every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pds_last_error() gives the message
+ *     (thread-local).  No C++ types or exceptions cross the boundary.
+ *   - images are fp32, planar, (B, C, H, W) contiguous — the reference layout (C,H,W) with a
+ *     leading batch of independent restorations; gray images have C = 1.
+ *   - `*_dev` pointers are CUDA device pointers on the handle's device, `*_host` are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - a handle owns its workspace (allocated in pds_create / pds_load_dncnn, nothing afterwards);
+ *     it is not thread-safe: one handle per stream.
+ *   - there is no CPU fallback: if no CUDA device is usable every call fails with an error.
+ */
+#ifndef PNP_PDS_H_
+#define PNP_PDS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDS_ABI_VERSION 1
+
+typedef struct pds_handle_s* pds_handle_t;
+typedef void* pds_stream_t;
+
+/* deg_op of operators.get_observation_operators (operators.py:60-79) */
+enum { PDS_OP_ID = 0, PDS_OP_BLUR = 1, PDS_OP_RANDOM_SAMPLING = 2 };
+
+/* method branches of iteration.test_iter (iteration.py:48-63, 71-73, 100-105) */
+enum {
+  PDS_METHOD_A = 0,   /* A-Proposed / ours-A : iteration.py:48-52 */
+  PDS_METHOD_B = 1,   /* B-Proposed / ours-B : iteration.py:53-58 */
+  PDS_METHOD_C = 2,   /* C-Proposed / ours-C : iteration.py:59-63 */
+  PDS_METHOD_FBS = 3, /* A-PnPFBS-DnCNN / comparisonA-1 : iteration.py:71-73 */
+  PDS_METHOD_RED = 4  /* A-RED-DnCNN / comparisonA-6 : iteration.py:100-105 */
+};
+
+/* engine used for the 64->64 channel layers of the denoiser */
+enum {
+  PDS_CONV_TCGEN05 = 0, /* TMA-fed tcgen05 implicit GEMM, fp16 hi/lo split operands, fp32 TMEM accumulators */
+  PDS_CONV_SIMT = 1     /* fp32 CUDA-core direct convolution (cross-check engine) */
+};
+
+typedef struct {
+  int32_t batch;        /* B: independent restorations (images x grid points) */
+  int32_t channels;     /* C: 1 or 3 (reference ch) */
+  int32_t height;       /* H = shape[-2] */
+  int32_t width;        /* W = shape[-1] */
+  int32_t method;       /* PDS_METHOD_* */
+  int32_t deg_op;       /* PDS_OP_* */
+  int32_t max_iter;     /* capacity of the per-iteration traces */
+  int32_t conv_engine;  /* PDS_CONV_* */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t denoiser_chunk; /* images per denoiser pass (0 = library default) */
+} pds_config_t;
+
+/* per-item hyper-parameters (one restoration = one item), all precomputed on the host:
+ *   epsilon = sqrt(n (1-sp_nl)) r alpha_n gaussian_nl      (operators.py:104)
+ *   eta     = alpha_s n sp_nl r / 2                        (operators.py:96)
+ * gamma1/gamma2/lambda/alpha as passed to iteration.test_iter (iteration.py:10). */
+typedef struct {
+  float gamma1;
+  float gamma2;
+  float epsilon;
+  float eta;
+  float lambda;   /* myLambda */
+  float alpha;    /* poisson_alpha */
+} pds_item_params_t;
+
+/* Number of double-precision partial sums recorded per item per iteration. */
+#define PDS_TRACE_WIDTH 4
+/* trace[it][b][0] = ||t||^2  with y = sigma t the dual variable before the l2-ball scaling (methods A, B)
+ * trace[it][b][1] = ||x_{k+1} - x_k||^2      numerator of c[i]      (iteration.py:187)
+ * trace[it][b][2] = ||x_k||^2                denominator of c[i]
+ * trace[it][b][3] = ||x_{k+1} - x_true||^2   n * mse of eval_psnr   (utils_eval.py:4-7) */
+
+const char* pds_last_error(void);
+int pds_abi_version(void);
+/* number of usable CUDA devices (0 if none); never fails */
+int pds_device_count(void);
+
+/* lifetime — replaces the per-call state set-up of iteration.test_iter (iteration.py:23-41) */
+int pds_create(const pds_config_t* cfg, pds_handle_t* out);
+int pds_destroy(pds_handle_t h);
+
+/* blur kernel h (l x l, row-major float64 as stored in blur_models/*.mat; operators.py:77-78) */
+int pds_set_blur_kernel(pds_handle_t h, const double* kernel_host, int l);
+/* keep-mask (H*W bytes, 1 = observed) of get_random_sampling_operator (operators.py:40-58);
+ * generated on the host with numpy's legacy MT19937 so it is bit-exact */
+int pds_set_mask(pds_handle_t h, const uint8_t* mask_host);
+/* n == batch, or n == 1 to broadcast */
+int pds_set_item_params(pds_handle_t h, const pds_item_params_t* params_host, int n);
+/* PDSW weight blob (models/weights.py) — replaces Denoiser.__init__/load_network (denoiser.py:9-32) */
+int pds_load_dncnn(pds_handle_t h, const void* blob_host, size_t nbytes);
+
+/* ---- stand-alone operators (device pointers, (B,C,H,W) fp32) ---- */
+/* phi / adj_phi of get_observation_operators (operators.py:60-79) for the handle's deg_op */
+int pds_phi(pds_handle_t h, const float* in_dev, float* out_dev, pds_stream_t stream);
+int pds_phi_adj(pds_handle_t h, const float* in_dev, float* out_dev, pds_stream_t stream);
+/* proj_l2_ball (operators.py:102-108) with the radius precomputed; per item, all channels jointly */
+int pds_proj_l2_ball(pds_handle_t h, const float* x_dev, const float* center_dev, float epsilon,
+                     float* out_dev, pds_stream_t stream);
+/* proj_l1_ball (operators.py:94-100) with the radius precomputed; per item */
+int pds_proj_l1_ball(pds_handle_t h, const float* x_dev, float eta, float* out_dev, pds_stream_t stream);
+/* prox_GKL (operators.py:114-115) */
+int pds_prox_gkl(pds_handle_t h, const float* x_dev, const float* x0_dev, float gamma, float alpha,
+                 float* out_dev, pds_stream_t stream);
+/* Denoiser.denoise (denoiser.py:14-16,34-46) / KAIR DnCNN.forward (network_dncnn.py:75-77) */
+int pds_dncnn_forward(pds_handle_t h, const float* in_dev, float* out_dev, pds_stream_t stream);
+
+/* ---- the resident loop: iteration.test_iter (iteration.py:44-189) ---- */
+/* copy x_0, x_obsrv (and x_true, may be NULL) into the handle, zero the dual/sparse state and traces */
+int pds_set_problem(pds_handle_t h, const float* x0_dev, const float* obs_dev, const float* xtrue_dev,
+                    pds_stream_t stream);
+/* run n_iter more iterations (asynchronous on `stream`) */
+int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream);
+int pds_iterations_done(pds_handle_t h);
+/* x_n, s_n (without the reference's +0.5, iteration.py:196), y_n = sigma t; any pointer may be NULL */
+int pds_get_state(pds_handle_t h, float* x_dev, float* s_dev, float* y_dev, pds_stream_t stream);
+/* synchronises `stream`; writes iterations_done*B*PDS_TRACE_WIDTH doubles */
+int pds_get_traces(pds_handle_t h, double* trace_host, size_t capacity_doubles, pds_stream_t stream);
+
+/* ---- host-buffer entry point: one whole restoration job, H2D and D2H inside ---- */
+/* equivalent of one iteration.test_iter call per item (iteration.py:10-196):
+ * inputs (B,C,H,W) fp32 on the host; outputs x (and s, may be NULL) and the traces */
+int pds_restore_host(pds_handle_t h, const float* x0_host, const float* obs_host, const float* xtrue_host,
+                     int n_iter, float* x_out_host, float* s_out_host, double* trace_host,
+                     size_t trace_capacity_doubles, pds_stream_t stream);
+
+/* ---- introspection for tests / bench ---- */
+/* kernels launched by this handle since creation */
+long long pds_kernel_launches(pds_handle_t h);
+/* bytes of device workspace owned by the handle */
+size_t pds_workspace_bytes(pds_handle_t h);
+
+/* ---- test hooks (hardware probes used by tests/test_gpu_tcgen05.py; not part of the drop-in surface) ---- */
+/* bit 0: put (start_address >> 7) & 7 in the A descriptor's base_offset field */
+int pds_debug_set_tc_variant(pds_handle_t h, int variant);
+/* one tcgen05.mma (M=128, N=16, K=16, B = identity) over a shared-memory region whose 16-byte chunk c
+ * holds (c & 1023, c >> 10) repeated; out_host[128][16] therefore reveals which chunk fed every (row, k) */
+int pds_debug_umma_probe(unsigned a_off, unsigned sbo, unsigned base_off, unsigned region_bytes, float* out_host);
+/* one activation-tile TMA box load at (x, y, plane_index); out_host receives the 36864 shared-memory bytes */
+int pds_debug_tma_probe(const void* act_dev, int nimg, int H, int W, int x, int y, int plane_index, void* out_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNP_PDS_H_ */

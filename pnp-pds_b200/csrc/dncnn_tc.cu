@@ -1,0 +1,481 @@
+// DnCNN 64->64 3x3 layers as a TMA-fed tcgen05 implicit GEMM (sm_100a).
+//
+// Reference: models/basic_models.py:31-35 (conv_list[i] + LeakyReLU), the only dense contraction
+// on the PnP-PDS path: per layer  D[pixel, oc] = sum_{tap, ci} A[pixel+tap, ci] W[oc, tap, ci].
+//
+// Mapping
+//   * one CTA tile = 16 rows x 8 pixels = 128 output pixels = UMMA M; N = 64 output channels;
+//     K = 64 input channels per tap, 9 taps -> 36 k-steps of 16.
+//   * operands are fp16 hi/lo splits (a = a_hi + a_lo, w = w_hi + w_lo); the kernel issues
+//     a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into ONE fp32 TMEM accumulator (108 tcgen05.mma per tile),
+//     which recovers ~2^-22 relative operand precision — needed for the 1e-4 iterate gate
+//     (single-pass fp16 misses it).
+//   * the activation halo tile (18 rows x 16 pixels x 64 ch, one per hi/lo plane) is fetched by
+//     ONE 4-D TMA box each with SWIZZLE_128B; out-of-image pixels are zero-filled by TMA, which is
+//     exactly the convolution's zero padding.  All 9 taps read that single tile: the A descriptor
+//     of tap (dy,dx) starts at pixel-row offset (dy*16+dx)*128 B with SBO = one tile row (2048 B).
+//   * the layer's weights (2 x 9 x 64x64 fp16, pre-swizzled on the host) stay resident in shared
+//     memory for the whole persistent CTA (147 KB), loaded once with cp.async.bulk.
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//     warps 2-5 = epilogue (tcgen05.ld -> bias + LeakyReLU -> hi/lo split -> 16-byte stores).
+//     The accumulator is double-buffered in TMEM (2 x 64 columns) so the epilogue of tile i
+//     overlaps the MMAs of tile i+1; the hi and lo planes have separate full/empty barriers so
+//     the next tile's hi plane streams in while the lo-plane MMAs of the current tile run.
+#include <cuda.h>
+
+#include "kernels.cuh"
+
+namespace pds {
+
+namespace {
+
+constexpr int kTileRows = 16, kTileCols = 8;          // output tile (M = 128)
+constexpr int kHaloRows = 18, kHaloPitch = 16;        // pixels
+constexpr uint32_t kPlaneBytes = kHaloRows * kHaloPitch * 128;   // 36864
+constexpr uint32_t kWTile = 64 * 128;                             // 8192: one (split, tap) 64x64 fp16 tile
+constexpr uint32_t kWBytes = 2 * 9 * kWTile;                      // 147456
+constexpr uint32_t kOffW = 0, kOffA0 = kWBytes, kOffA1 = kOffA0 + kPlaneBytes, kOffBar = kOffA1 + kPlaneBytes;
+constexpr uint32_t kOffBias = kOffBar + 128, kSmemUsed = kOffBias + 256;
+constexpr uint32_t kSmemBytes = kSmemUsed + 1024;                 // slack for manual 1024-B alignment
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 128;
+constexpr uint32_t kIdesc = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct TcArgs {
+  const __half* w_img;
+  const float* bias;
+  __half* out;
+  float slope;
+  int H, W, nimg, tiles_x, tiles_y, ntiles;
+  int variant;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor").
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t base_off) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(base_off & 7u) << 49) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void store_half_row(__half* dst_hi, __half* dst_lo, const uint32_t (&r)[32], const float* bias_s, int c0,
+                                               float slope) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 hi, lo;
+    __half2* h = reinterpret_cast<__half2*>(&hi);
+    __half2* l = reinterpret_cast<__half2*>(&lo);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = q * 8 + 2 * k;
+      const float v0 = leaky(__uint_as_float(r[c]) + bias_s[c0 + c], slope);
+      const float v1 = leaky(__uint_as_float(r[c + 1]) + bias_s[c0 + c + 1], slope);
+      __half h0, l0, h1, l1;
+      split_hi_lo(v0, h0, l0);
+      split_hi_lo(v1, h1, l1);
+      h[k] = __halves2half2(h0, h1);
+      l[k] = __halves2half2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(dst_hi + c0 + q * 8) = hi;
+    *reinterpret_cast<uint4*>(dst_lo + c0 + q * 8) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sW = base + kOffW, sA[2] = {base + kOffA0, base + kOffA1}, sBar = base + kOffBar;
+  const uint32_t bFull[2] = {sBar + 0, sBar + 8}, bEmpty[2] = {sBar + 16, sBar + 24}, bW = sBar + 32;
+  const uint32_t bTFull[2] = {sBar + 40, sBar + 48}, bTEmpty[2] = {sBar + 56, sBar + 64};
+  const uint32_t sTmemSlot = sBar + 80;
+  float* bias_s = reinterpret_cast<float*>(gbase + kOffBias);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(bFull[0], 1); mbar_init(bFull[1], 1);
+    mbar_init(bEmpty[0], 1); mbar_init(bEmpty[1], 1);
+    mbar_init(bW, 1);
+    mbar_init(bTFull[0], 1); mbar_init(bTFull[1], 1);
+    mbar_init(bTEmpty[0], 4); mbar_init(bTEmpty[1], 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar + 80);
+
+  const int per_img = a.tiles_x * a.tiles_y;
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bW, kWBytes);
+      for (int i = 0; i < 18; ++i) bulk_load(sW + i * kWTile, reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)i * kWTile, kWTile, bW);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        const int img = tile / per_img, rem = tile - img * per_img;
+        const int y0 = (rem / a.tiles_x) * kTileRows, x0 = (rem % a.tiles_x) * kTileCols;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          mbar_wait(bEmpty[p], (uint32_t)((it & 1) ^ 1));
+          mbar_expect_tx(bFull[p], kPlaneBytes);
+          tma_load_4d(sA[p], &tmap, bFull[p], 0, x0 - 1, y0 - 1, img * 2 + p);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      mbar_wait(bW, 0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(bTEmpty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64u;
+        uint32_t accumulate = 0;
+#pragma unroll 1
+        for (int p = 0; p < 2; ++p) {
+          mbar_wait(bFull[p], (uint32_t)(it & 1));
+          tc_fence_after();
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a_row = sA[p] + (uint32_t)(dy * kHaloPitch + dx) * 128u;
+            const uint32_t boff = (a.variant & 1) ? ((a_row >> 7) & 7u) : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ad = make_desc(a_row + k * 32, kHaloPitch * 128, boff);
+              const uint64_t bd_hi = make_desc(sW + (uint32_t)tap * kWTile + k * 32, 1024, 0);
+              umma_f16(d_tmem, ad, bd_hi, kIdesc, accumulate);
+              accumulate = 1;
+              if (p == 0) {
+                const uint64_t bd_lo = make_desc(sW + (uint32_t)(9 + tap) * kWTile + k * 32, 1024, 0);
+                umma_f16(d_tmem, ad, bd_lo, kIdesc, 1);
+              }
+            }
+          }
+          umma_commit(bEmpty[p]);     // plane p may be overwritten once these MMAs retire
+        }
+        umma_commit(bTFull[acc]);     // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    const size_t hw = (size_t)a.H * a.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
+      const int acc = it & 1;
+      mbar_wait(bTFull[acc], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 64u;
+      uint32_t r0[32], r1[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty[acc]);
+      if (y < a.H && x < a.W) {
+        const size_t pix = (size_t)y * a.W + x;
+        __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+        __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
+        store_half_row(o_hi, o_lo, r0, bias_s, 0, a.slope);
+        store_half_row(o_hi, o_lo, r1, bias_s, 32, a.slope);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Probes (test hooks): establish, on hardware, how a tcgen05 shared-memory descriptor addresses
+// memory, and what a TMA box load leaves in shared memory.
+// ---------------------------------------------------------------------------------------------
+struct ProbeArgs {
+  uint32_t a_off, sbo, base_off, region_bytes;
+  float* out;   // [128][16]
+};
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(ProbeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  // region [0, region_bytes): A pattern; then 2 KiB B tile; then barrier + tmem slot
+  __half* A = reinterpret_cast<__half*>(g);
+  const uint32_t nchunk = a.region_bytes / 16;
+  for (uint32_t c = threadIdx.x; c < nchunk; c += blockDim.x)
+    for (int e = 0; e < 8; ++e) A[c * 8 + e] = __float2half_rn((e & 1) ? (float)(c >> 10) : (float)(c & 1023u));
+  __half* B = reinterpret_cast<__half*>(g + a.region_bytes);
+  for (uint32_t i = threadIdx.x; i < 16 * 64; i += blockDim.x) {
+    const uint32_t n = i / 64, kk = i % 64;               // logical B[n][kk]
+    const uint32_t chunk = (kk >> 3) ^ (n & 7);
+    B[n * 64 + chunk * 8 + (kk & 7)] = __float2half_rn(kk == n ? 1.f : 0.f);
+  }
+  const uint32_t sBar = base + a.region_bytes + 2048, sSlot = sBar + 16;
+  if (threadIdx.x == 0) {
+    mbar_init(sBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sSlot), "r"(32u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(g + a.region_bytes + 2048 + 16);
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t ad = make_desc(base + a.a_off, a.sbo, a.base_off);
+    const uint64_t bd = make_desc(base + a.region_bytes, 1024, 0);
+    umma_f16(tmem_base, ad, bd, idesc, 0);
+    umma_commit(sBar);
+  }
+  mbar_wait(sBar, 0);
+  tc_fence_after();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t r[16];
+  const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  tmem_ld_wait();
+  for (int j = 0; j < 16; ++j) a.out[(warp * 32 + lane) * 16 + j] = __uint_as_float(r[j]);
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u) : "memory");
+  }
+}
+
+__global__ void __launch_bounds__(128, 1) tma_probe_kernel(const __grid_constant__ CUtensorMap tmap, int c1, int c2, int c3,
+                                                           uint4* out /* kPlaneBytes/16 */) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* g = smem_raw + (base - raw);
+  const uint32_t sBar = base + kPlaneBytes;
+  if (threadIdx.x == 0) {
+    mbar_init(sBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(sBar, kPlaneBytes);
+    tma_load_4d(base, &tmap, sBar, 0, c1, c2, c3);
+  }
+  mbar_wait(sBar, 0);
+  const uint4* s = reinterpret_cast<const uint4*>(g);
+  for (uint32_t i = threadIdx.x; i < kPlaneBytes / 16; i += blockDim.x) out[i] = s[i];
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  PDS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg * 2};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  const cuuint32_t box[4] = {64, (cuuint32_t)kHaloPitch, (cuuint32_t)kHaloRows, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, act, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PDS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return 0;
+}
+
+}  // namespace
+
+struct TcPlan {
+  CUtensorMap map[2];
+  __half* act[2];
+  int nimg, H, W;
+  int num_sms;
+};
+
+int tc_num_sms() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+
+int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** out) {
+  TcPlan* p = new TcPlan();
+  p->act[0] = act0;
+  p->act[1] = act1;
+  p->nimg = nimg;
+  p->H = H;
+  p->W = W;
+  p->num_sms = tc_num_sms();
+  int rc = make_act_map(&p->map[0], act0, nimg, H, W);
+  if (!rc) rc = make_act_map(&p->map[1], act1, nimg, H, W);
+  if (!rc) {
+    cudaError_t e = cudaFuncSetAttribute(conv_mid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaFuncSetAttribute(conv_mid_tc_kernel): ") + cudaGetErrorString(e));
+      rc = 1;
+    }
+  }
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return 0;
+}
+
+void tc_plan_destroy(TcPlan* p) { delete p; }
+
+cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st) {
+  TcArgs a{};
+  a.w_img = L.w_mid_tc;
+  a.bias = L.bias;
+  a.out = plan->act[in_buf ^ 1];
+  a.slope = slope;
+  a.H = plan->H;
+  a.W = plan->W;
+  a.nimg = nimg;
+  a.tiles_x = (plan->W + kTileCols - 1) / kTileCols;
+  a.tiles_y = (plan->H + kTileRows - 1) / kTileRows;
+  a.ntiles = a.tiles_x * a.tiles_y * nimg;
+  a.variant = variant;
+  const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
+  conv_mid_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(plan->map[in_buf], a);
+  return cudaGetLastError();
+}
+
+}  // namespace pds
+
+// ---- debug exports (declared in include/pnp_pds.h under "test hooks") ----
+extern "C" int pds_debug_umma_probe(unsigned a_off, unsigned sbo, unsigned base_off, unsigned region_bytes, float* out_host /*128*16*/) {
+  using namespace pds;
+  PDS_REQUIRE(out_host && region_bytes % 1024 == 0 && region_bytes <= 200 * 1024, "bad probe arguments");
+  float* d = nullptr;
+  PDS_CUDA_OK(cudaMalloc(&d, 128 * 16 * sizeof(float)));
+  const size_t smem = (size_t)region_bytes + 2048 + 64 + 1024;
+  PDS_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ProbeArgs a{a_off, sbo, base_off, region_bytes, d};
+  umma_probe_kernel<<<1, 128, smem>>>(a);
+  PDS_CUDA_OK(cudaGetLastError());
+  PDS_CUDA_OK(cudaDeviceSynchronize());
+  PDS_CUDA_OK(cudaMemcpy(out_host, d, 128 * 16 * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}
+
+extern "C" int pds_debug_tma_probe(const void* act_dev, int nimg, int H, int W, int x, int y, int plane_index, void* out_host) {
+  using namespace pds;
+  CUtensorMap map;
+  int rc = make_act_map(&map, (__half*)act_dev, nimg, H, W);
+  if (rc) return rc;
+  uint4* d = nullptr;
+  PDS_CUDA_OK(cudaMalloc(&d, kPlaneBytes));
+  const size_t smem = (size_t)kPlaneBytes + 64 + 1024;
+  PDS_CUDA_OK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tma_probe_kernel<<<1, 128, smem>>>(map, x, y, plane_index, d);
+  PDS_CUDA_OK(cudaGetLastError());
+  PDS_CUDA_OK(cudaDeviceSynchronize());
+  PDS_CUDA_OK(cudaMemcpy(out_host, d, kPlaneBytes, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
+}

@@ -1,0 +1,91 @@
+// Internal launch interface between the C-ABI (pds_api.cu) and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace pds {
+
+struct Dims {
+  int B, C, H, W;
+  int hw;  // H*W
+  int n;   // C*H*W  (elements per item)
+};
+
+// Arguments shared by the fused primal / dual kernels.  Pointers are (B,C,H,W) fp32 unless noted.
+struct StepArgs {
+  Dims d;
+  int method;                // PDS_METHOD_A/B/C
+  const float* x;            // x_k
+  const float* xn;           // x_{k+1} (denoiser output)              [dual]
+  float* u;                  // denoiser input x_k - gamma1 Phi^T y_k   [primal]
+  float* t;                  // dual state, y = sigma t (A,B) or y (C); read in both, written in dual
+  const float* s_old;        // s_k          (B)
+  const float* s_new;        // s_{k+1}      (B)   [dual]
+  const float* obs;          // x_obsrv
+  const float* xtrue;        // may be null
+  const uint8_t* mask;       // (H*W) keep mask or null
+  const ItemParams* prm;     // [B]
+  const double* sums_prev;   // [B][NSUM] of the previous iteration (null on the first)
+  double* sums_cur;          // [B][NSUM] of this iteration          [dual]
+};
+
+// ---- pds_elementwise.cu: Phi in {Id, mask} ---------------------------------
+cudaError_t launch_primal_pointwise(const StepArgs& a, cudaStream_t st);
+cudaError_t launch_dual_pointwise(const StepArgs& a, cudaStream_t st);
+cudaError_t launch_mask_apply(const Dims& d, const float* in, const uint8_t* mask, float* out, cudaStream_t st);
+cudaError_t launch_scale_by_sigma(const Dims& d, const float* t, const ItemParams* prm, const double* sums, int method,
+                                  float* y, cudaStream_t st);
+// stand-alone prox operators
+cudaError_t launch_diff_norm2(const Dims& d, const float* x, const float* c, double* acc /*[B]*/, cudaStream_t st);
+cudaError_t launch_proj_l2_apply(const Dims& d, const float* x, const float* c, float eps, const double* acc, float* out,
+                                 cudaStream_t st);
+cudaError_t launch_prox_gkl(const Dims& d, const float* x, const float* x0, float gamma, float alpha, float* out,
+                            cudaStream_t st);
+// metrics for methods without a dual kernel: fills SUM_DX2, SUM_X2, SUM_ERR2
+cudaError_t launch_metrics(const Dims& d, const float* xn, const float* x, const float* xtrue, double* sums_cur,
+                           cudaStream_t st);
+// out = a*p + b*q + c*r   (r, q may be null)
+cudaError_t launch_axpbypcz(size_t n, float a, const float* p, float b, const float* q, float c, const float* r, float* out,
+                            cudaStream_t st);
+
+// ---- pds_blur.cu: Phi = periodic stencil -----------------------------------
+struct BlurTaps {            // device arrays, built by pds_set_blur_kernel
+  const float* w[2];         // [0] = Phi taps, [1] = Phi^T taps
+  const short2* off[2];      // (dy, dx) per tap: out[i,j] += w * in[i+dy, j+dx] (periodic)
+  int ntaps;
+  int ry, rx;                // max |dy|, max |dx|
+};
+cudaError_t launch_blur_apply(const Dims& d, const BlurTaps& taps, int adjoint, const float* in, float* out, cudaStream_t st);
+cudaError_t launch_primal_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);
+cudaError_t launch_dual_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);
+
+// ---- pds_l1ball.cu ----------------------------------------------------------
+// s_out = P_{l1-ball(eta)}(z), z = s_in - gamma1*sigma*t (t != null) or z = s_in.
+// eta per item from prm (eta_override < 0) or the scalar eta_override.
+cudaError_t launch_l1ball(const Dims& d, const float* s_in, const float* t, const ItemParams* prm, const double* sums_prev,
+                          float eta_override, float* s_out, float* tau_out /*[B] or null*/, cudaStream_t st);
+
+// ---- dncnn_*.cu ---------------------------------------------------------------
+// Activations between layers: [img][2 (hi,lo)][H][W][64] fp16 ("NHWC hi/lo planes").
+struct DncnnLayerW {
+  const float* w_first;   // [9*Cin][64]     (k = tap*Cin + ci)          first layer
+  const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
+  const __half* w_mid_tc; // smem image for the tcgen05 engine: [2 (hi,lo)][9][64 oc][64 ci] fp16, 128B-swizzled rows
+  const float* w_last;    // [Cout][9][64 ci]                            last layer
+  const float* bias;      // [Cout of this layer]
+};
+cudaError_t launch_conv_first(int nimg, int C, int H, int W, const float* in /*(nimg,C,H,W)*/, const DncnnLayerW& L, float slope,
+                              int clamp_in, __half* act_out, cudaStream_t st);
+cudaError_t launch_conv_mid_simt(int nimg, int H, int W, const __half* act_in, const DncnnLayerW& L, float slope, __half* act_out,
+                                 cudaStream_t st);
+cudaError_t launch_conv_last(int nimg, int C, int H, int W, const __half* act_in, const DncnnLayerW& L, const float* net_in,
+                             float residual_sign, int clamp, float* out, cudaStream_t st);
+
+// tcgen05 engine (dncnn_tc.cu)
+struct TcPlan;  // opaque: tensor maps for the two activation buffers
+int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** out);  // returns 0 / error (message set)
+void tc_plan_destroy(TcPlan* p);
+// in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
+cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
+int tc_num_sms();
+
+}  // namespace pds

@@ -1,0 +1,586 @@
+// C-ABI of libpnp_pds.so: handle management, weight/operator set-up, stand-alone operators and
+// the resident PnP-PDS loop.  See include/pnp_pds.h for the contract and the reference
+// interfaces each entry point replaces.
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace pds {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+}  // namespace pds
+
+using namespace pds;
+
+struct pds_handle_s {
+  pds_config_t cfg{};
+  Dims d{};
+  // state of iteration.test_iter (iteration.py:23-32)
+  float* xbuf[2] = {nullptr, nullptr};
+  float* u = nullptr;
+  float* t = nullptr;
+  float* sbuf[2] = {nullptr, nullptr};
+  float* obs = nullptr;
+  float* xtrue = nullptr;
+  float* tmp[2] = {nullptr, nullptr};
+  bool have_true = false, have_problem = false;
+  int cur = 0, scur = 0, iter = 0;
+  uint8_t* mask = nullptr;
+  bool have_mask = false;
+  ItemParams* prm = nullptr;
+  bool have_params = false;
+  double* sums = nullptr;      // [max_iter][B][NSUM]
+  double* scratch = nullptr;   // [B]
+  // blur
+  BlurTaps taps{};
+  bool have_blur = false;
+  // denoiser
+  bool have_net = false;
+  int depth = 0;
+  float slope = 0.f, res_sign = 1.f;
+  int clamp = 1;
+  std::vector<DncnnLayerW> layers;
+  __half* act[2] = {nullptr, nullptr};
+  int chunk = 1;
+  TcPlan* tc = nullptr;
+  int tc_variant = 0;
+  // bookkeeping
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  long long launches = 0;
+};
+
+namespace {
+
+template <typename T>
+int dev_alloc(pds_handle_s* h, T** p, size_t count) {
+  void* q = nullptr;
+  size_t nb = count * sizeof(T);
+  if (nb == 0) nb = sizeof(T);
+  PDS_CUDA_OK(cudaMalloc(&q, nb));
+  h->allocs.push_back(q);
+  h->bytes += nb;
+  *p = static_cast<T*>(q);
+  return 0;
+}
+
+#define PDS_TRY(expr)         \
+  do {                        \
+    int _r = (expr);          \
+    if (_r != 0) return _r;   \
+  } while (0)
+
+#define PDS_LAUNCH(h, expr)   \
+  do {                        \
+    PDS_CUDA_OK(expr);        \
+    (h)->launches++;          \
+  } while (0)
+
+int check_handle(pds_handle_t h) {
+  PDS_REQUIRE(h != nullptr, "null handle");
+  PDS_CUDA_OK(cudaSetDevice(h->cfg.device));
+  return 0;
+}
+
+size_t total_elems(const pds_handle_s* h) { return (size_t)h->d.B * h->d.n; }
+
+int apply_phi(pds_handle_s* h, bool adjoint, const float* in, float* out, cudaStream_t st) {
+  switch (h->cfg.deg_op) {
+    case PDS_OP_ID:
+      if (in != out) PDS_CUDA_OK(cudaMemcpyAsync(out, in, total_elems(h) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return 0;
+    case PDS_OP_BLUR:
+      PDS_REQUIRE(h->have_blur, "blur kernel not set (pds_set_blur_kernel)");
+      PDS_REQUIRE(in != out, "blur cannot run in place");
+      PDS_LAUNCH(h, launch_blur_apply(h->d, h->taps, adjoint ? 1 : 0, in, out, st));
+      return 0;
+    case PDS_OP_RANDOM_SAMPLING:
+      PDS_REQUIRE(h->have_mask, "sampling mask not set (pds_set_mask)");
+      PDS_LAUNCH(h, launch_mask_apply(h->d, in, h->mask, out, st));
+      return 0;
+  }
+  PDS_REQUIRE(false, "unknown deg_op");
+}
+
+// Denoiser.denoise over all B items, `chunk` images per pass so that activations can stay in L2.
+int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
+  PDS_REQUIRE(h->have_net, "denoiser weights not loaded (pds_load_dncnn)");
+  const Dims& d = h->d;
+  for (int b0 = 0; b0 < d.B; b0 += h->chunk) {
+    const int nimg = (d.B - b0 < h->chunk) ? d.B - b0 : h->chunk;
+    const float* cin = in + (size_t)b0 * d.n;
+    float* cout = out + (size_t)b0 * d.n;
+    PDS_LAUNCH(h, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
+    int src = 0;
+    for (int l = 1; l < h->depth - 1; ++l) {
+      if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+        PDS_LAUNCH(h, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
+      } else {
+        PDS_LAUNCH(h, launch_conv_mid_simt(nimg, d.H, d.W, h->act[src], h->layers[l], h->slope, h->act[src ^ 1], st));
+      }
+      src ^= 1;
+    }
+    PDS_LAUNCH(h, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
+  }
+  return 0;
+}
+
+StepArgs step_args(pds_handle_s* h) {
+  StepArgs a{};
+  a.d = h->d;
+  a.method = h->cfg.method;
+  a.x = h->xbuf[h->cur];
+  a.xn = h->xbuf[h->cur ^ 1];
+  a.u = h->u;
+  a.t = h->t;
+  a.s_old = h->sbuf[h->scur];
+  a.s_new = h->sbuf[h->scur ^ 1];
+  a.obs = h->obs;
+  a.xtrue = h->have_true ? h->xtrue : nullptr;
+  a.mask = (h->cfg.deg_op == PDS_OP_RANDOM_SAMPLING) ? h->mask : nullptr;
+  a.prm = h->prm;
+  const size_t row = (size_t)h->d.B * NSUM;
+  a.sums_prev = h->iter > 0 ? h->sums + (size_t)(h->iter - 1) * row : nullptr;
+  a.sums_cur = h->sums + (size_t)h->iter * row;
+  return a;
+}
+
+// One iteration of A-/B-/C-Proposed (iteration.py:48-63).
+int pds_iteration(pds_handle_s* h, cudaStream_t st) {
+  StepArgs a = step_args(h);
+  const bool blur = h->cfg.deg_op == PDS_OP_BLUR;
+  // x_{k+1} = D(x_k - gamma1 Phi^T y_k)
+  if (blur) PDS_LAUNCH(h, launch_primal_blur(a, h->taps, st));
+  else PDS_LAUNCH(h, launch_primal_pointwise(a, st));
+  // s_{k+1} = P_l1(s_k - gamma1 y_k)
+  if (h->cfg.method == PDS_METHOD_B)
+    PDS_LAUNCH(h, launch_l1ball(h->d, a.s_old, h->t, h->prm, a.sums_prev, -1.f, h->sbuf[h->scur ^ 1], nullptr, st));
+  PDS_TRY(run_dncnn(h, h->u, h->xbuf[h->cur ^ 1], st));
+  // y_{k+1}
+  if (blur) PDS_LAUNCH(h, launch_dual_blur(a, h->taps, st));
+  else PDS_LAUNCH(h, launch_dual_pointwise(a, st));
+  h->cur ^= 1;
+  if (h->cfg.method == PDS_METHOD_B) h->scur ^= 1;
+  h->iter++;
+  return 0;
+}
+
+// u = x - coef * v  with coef = g1*lam per item (A-PnPFBS-DnCNN) — small helper kernel
+__global__ void fbs_combine_kernel(Dims d, const float* __restrict__ x, const float* __restrict__ v, const ItemParams* prm, int mode,
+                                   const float* __restrict__ dx, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const ItemParams p = prm[b];
+  const size_t base = (size_t)b * d.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.n; i += gridDim.x * blockDim.x) {
+    const size_t g = base + i;
+    if (mode == 0) {
+      // iteration.py:73: x - gamma1*myLambda*0.5*(2 Phi^T(Phi x - b))
+      out[g] = fmaf(-p.g1 * p.lam, v[g], x[g]);
+    } else {
+      // iteration.py:102-105: mu = 2/(1/g1^2 + lam); x - mu*((1/g1^2) Phi^T(Phi x - b) + lam (x - D(x)))
+      const float ig = 1.f / (p.g1 * p.g1);
+      const float mu = 2.f / (ig + p.lam);
+      out[g] = x[g] - mu * (ig * v[g] + p.lam * (x[g] - dx[g]));
+    }
+  }
+}
+
+// A-PnPFBS-DnCNN (iteration.py:71-73) and A-RED-DnCNN (iteration.py:100-105)
+int fbs_red_iteration(pds_handle_s* h, cudaStream_t st) {
+  const Dims& d = h->d;
+  float* x = h->xbuf[h->cur];
+  float* xn = h->xbuf[h->cur ^ 1];
+  const size_t n = total_elems(h);
+  // tmp0 = Phi x - b ; tmp1 = Phi^T tmp0
+  PDS_TRY(apply_phi(h, false, x, h->tmp[0], st));
+  PDS_LAUNCH(h, launch_axpbypcz(n, 1.f, h->tmp[0], -1.f, h->obs, 0.f, nullptr, h->tmp[0], st));
+  if (h->cfg.deg_op == PDS_OP_ID) {
+    PDS_CUDA_OK(cudaMemcpyAsync(h->tmp[1], h->tmp[0], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    PDS_TRY(apply_phi(h, true, h->tmp[0], h->tmp[1], st));
+  }
+  dim3 grid((d.n + 1023) / 1024 > 148 * 4 ? 148 * 4 : (d.n + 1023) / 1024, d.B);
+  if (h->cfg.method == PDS_METHOD_FBS) {
+    fbs_combine_kernel<<<grid, 256, 0, st>>>(d, x, h->tmp[1], h->prm, 0, nullptr, h->u);
+    PDS_LAUNCH(h, cudaGetLastError());
+    PDS_TRY(run_dncnn(h, h->u, xn, st));
+  } else {
+    PDS_TRY(run_dncnn(h, x, h->u, st));   // u = D(x)
+    fbs_combine_kernel<<<grid, 256, 0, st>>>(d, x, h->tmp[1], h->prm, 1, h->u, xn);
+    PDS_LAUNCH(h, cudaGetLastError());
+  }
+  const size_t row = (size_t)d.B * NSUM;
+  PDS_LAUNCH(h, launch_metrics(d, xn, x, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  h->cur ^= 1;
+  h->iter++;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pds_last_error(void) { return g_err.c_str(); }
+int pds_abi_version(void) { return PDS_ABI_VERSION; }
+
+int pds_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
+  PDS_REQUIRE(cfg && out, "null argument");
+  PDS_REQUIRE(cfg->batch >= 1 && cfg->height >= 1 && cfg->width >= 1, "bad shape");
+  PDS_REQUIRE(cfg->channels == 1 || cfg->channels == 3, "channels must be 1 or 3 (reference ch)");
+  PDS_REQUIRE(cfg->method >= PDS_METHOD_A && cfg->method <= PDS_METHOD_RED, "unknown method");
+  PDS_REQUIRE(cfg->deg_op >= PDS_OP_ID && cfg->deg_op <= PDS_OP_RANDOM_SAMPLING, "unknown deg_op");
+  PDS_REQUIRE(cfg->max_iter >= 1, "max_iter must be >= 1");
+  PDS_REQUIRE((long long)cfg->batch * cfg->channels <= 65535, "batch*channels exceeds the grid limit");
+  PDS_REQUIRE(pds_device_count() > cfg->device && cfg->device >= 0,
+              "no usable CUDA device: this library has no CPU fallback");
+  PDS_CUDA_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop{};
+  PDS_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  PDS_REQUIRE(prop.major == 10, "libpnp_pds is built for sm_100a (B200) only");
+  pds_handle_s* h = new (std::nothrow) pds_handle_s();
+  PDS_REQUIRE(h, "out of host memory");
+  h->cfg = *cfg;
+  h->d = Dims{cfg->batch, cfg->channels, cfg->height, cfg->width, cfg->height * cfg->width,
+              cfg->channels * cfg->height * cfg->width};
+  const size_t n = total_elems(h);
+  int rc = 0;
+  auto A = [&](auto** p, size_t c) { if (!rc) rc = dev_alloc(h, p, c); };
+  A(&h->xbuf[0], n); A(&h->xbuf[1], n); A(&h->u, n); A(&h->t, n);
+  A(&h->obs, n); A(&h->xtrue, n);
+  if (cfg->method == PDS_METHOD_B) { A(&h->sbuf[0], n); A(&h->sbuf[1], n); }
+  if (cfg->method == PDS_METHOD_FBS || cfg->method == PDS_METHOD_RED) { A(&h->tmp[0], n); A(&h->tmp[1], n); }
+  A(&h->mask, (size_t)h->d.hw);
+  A(&h->prm, (size_t)cfg->batch);
+  A(&h->sums, (size_t)cfg->max_iter * cfg->batch * NSUM);
+  A(&h->scratch, (size_t)cfg->batch);
+  if (rc) { pds_destroy(h); return rc; }
+  *out = h;
+  return 0;
+}
+
+int pds_destroy(pds_handle_t h) {
+  if (!h) return 0;
+  cudaSetDevice(h->cfg.device);
+  if (h->tc) tc_plan_destroy(h->tc);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return 0;
+}
+
+int pds_set_blur_kernel(pds_handle_t h, const double* k, int l) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(k && l >= 1 && l <= 63 && (l % 2 == 1), "blur kernel must be l x l with odd l <= 63");
+  PDS_REQUIRE(!h->have_blur, "blur kernel already set");
+  const int c = l / 2;
+  std::vector<float> w;
+  std::vector<short2> off[2];
+  int ry = 0, rx = 0;
+  for (int a = 0; a < l; ++a)
+    for (int b = 0; b < l; ++b) {
+      const double v = k[a * l + b];
+      if (v == 0.0) continue;
+      w.push_back((float)v);
+      off[0].push_back(make_short2((short)(c - a), (short)(c - b)));  // Phi   (operators.py:7-22)
+      off[1].push_back(make_short2((short)(a - c), (short)(b - c)));  // Phi^T (operators.py:24-38)
+      ry = std::max(ry, std::abs(a - c));
+      rx = std::max(rx, std::abs(b - c));
+    }
+  PDS_REQUIRE(!w.empty(), "blur kernel is all zeros");
+  float* dw = nullptr;
+  PDS_TRY(dev_alloc(h, &dw, w.size()));
+  PDS_CUDA_OK(cudaMemcpy(dw, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+  for (int q = 0; q < 2; ++q) {
+    short2* dof = nullptr;
+    PDS_TRY(dev_alloc(h, &dof, off[q].size()));
+    PDS_CUDA_OK(cudaMemcpy(dof, off[q].data(), off[q].size() * sizeof(short2), cudaMemcpyHostToDevice));
+    h->taps.w[q] = dw;
+    h->taps.off[q] = dof;
+  }
+  h->taps.ntaps = (int)w.size();
+  h->taps.ry = ry;
+  h->taps.rx = rx;
+  h->have_blur = true;
+  return 0;
+}
+
+int pds_set_mask(pds_handle_t h, const uint8_t* mask_host) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(mask_host, "null mask");
+  PDS_CUDA_OK(cudaMemcpy(h->mask, mask_host, (size_t)h->d.hw, cudaMemcpyHostToDevice));
+  h->have_mask = true;
+  return 0;
+}
+
+int pds_set_item_params(pds_handle_t h, const pds_item_params_t* p, int n) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(p && (n == 1 || n == h->d.B), "params: n must be 1 or batch");
+  std::vector<ItemParams> v(h->d.B);
+  for (int b = 0; b < h->d.B; ++b) {
+    const pds_item_params_t& q = p[n == 1 ? 0 : b];
+    v[b] = ItemParams{q.gamma1, q.gamma2, q.epsilon, q.eta, q.lambda, q.alpha};
+  }
+  PDS_CUDA_OK(cudaMemcpy(h->prm, v.data(), v.size() * sizeof(ItemParams), cudaMemcpyHostToDevice));
+  h->have_params = true;
+  return 0;
+}
+
+int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(!h->have_net, "denoiser already loaded");
+  PDS_REQUIRE(blob && nbytes >= 48, "weight blob too small");
+  const unsigned char* p = static_cast<const unsigned char*>(blob);
+  PDS_REQUIRE(std::memcmp(p, "PDSW", 4) == 0, "not a PDSW weight blob");
+  int32_t hdr[5];
+  std::memcpy(hdr, p + 4, sizeof(hdr));
+  float fl[2];
+  std::memcpy(fl, p + 24, sizeof(fl));
+  int32_t clampv;
+  std::memcpy(&clampv, p + 32, 4);
+  const int ver = hdr[0], depth = hdr[1], cin = hdr[2], nch = hdr[3], cout = hdr[4];
+  PDS_REQUIRE(ver == 1, "unsupported PDSW version");
+  PDS_REQUIRE(depth >= 3 && depth <= 64, "unsupported depth");
+  PDS_REQUIRE(nch == kMid, "only 64-channel DnCNN bodies are supported (all reference checkpoints)");
+  PDS_REQUIRE(cin == h->d.C && cout == h->d.C, "checkpoint channel count does not match the handle (ch)");
+  size_t need = 48;
+  for (int l = 0; l < depth; ++l) {
+    const int ci = l == 0 ? cin : nch, co = l == depth - 1 ? cout : nch;
+    need += (size_t)(co * ci * 9 + co) * 4;
+  }
+  PDS_REQUIRE(need == nbytes, "PDSW blob size mismatch");
+  h->depth = depth;
+  h->slope = fl[0];
+  h->res_sign = fl[1];
+  h->clamp = clampv;
+  h->layers.assign(depth, DncnnLayerW{});
+  const float* src = reinterpret_cast<const float*>(p + 48);
+  std::vector<float> buf;
+  for (int l = 0; l < depth; ++l) {
+    const int ci = l == 0 ? cin : nch, co = l == depth - 1 ? cout : nch;
+    const float* w = src;                // [co][ci][3][3]
+    const float* b = src + (size_t)co * ci * 9;
+    src = b + co;
+    DncnnLayerW& L = h->layers[l];
+    float* db = nullptr;
+    PDS_TRY(dev_alloc(h, &db, (size_t)co));
+    PDS_CUDA_OK(cudaMemcpy(db, b, (size_t)co * 4, cudaMemcpyHostToDevice));
+    L.bias = db;
+    if (l == 0) {
+      buf.assign((size_t)9 * ci * 64, 0.f);
+      for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+          for (int tp = 0; tp < 9; ++tp) buf[((size_t)tp * ci + c) * 64 + o] = w[((size_t)o * ci + c) * 9 + tp];
+      float* dw = nullptr;
+      PDS_TRY(dev_alloc(h, &dw, buf.size()));
+      PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+      L.w_first = dw;
+    } else if (l == depth - 1) {
+      buf.assign((size_t)co * 9 * 64, 0.f);
+      for (int o = 0; o < co; ++o)
+        for (int c = 0; c < ci; ++c)
+          for (int tp = 0; tp < 9; ++tp) buf[((size_t)o * 9 + tp) * 64 + c] = w[((size_t)o * ci + c) * 9 + tp];
+      float* dw = nullptr;
+      PDS_TRY(dev_alloc(h, &dw, buf.size()));
+      PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+      L.w_last = dw;
+    } else {
+      // SIMT engine: [ci][tap][oc] fp32
+      buf.assign((size_t)64 * 9 * 64, 0.f);
+      for (int o = 0; o < 64; ++o)
+        for (int c = 0; c < 64; ++c)
+          for (int tp = 0; tp < 9; ++tp) buf[((size_t)c * 9 + tp) * 64 + o] = w[((size_t)o * 64 + c) * 9 + tp];
+      float* dw = nullptr;
+      PDS_TRY(dev_alloc(h, &dw, buf.size()));
+      PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+      L.w_mid = dw;
+      // tcgen05 engine: shared-memory image [split][tap][oc][ci] fp16, K-major rows of 128 B,
+      // 16-byte chunk j of row oc stored at chunk (j ^ (oc & 7))  (SWIZZLE_128B)
+      std::vector<__half> img((size_t)2 * 9 * 64 * 64);
+      for (int tp = 0; tp < 9; ++tp)
+        for (int o = 0; o < 64; ++o)
+          for (int c = 0; c < 64; ++c) {
+            const float v = w[((size_t)o * 64 + c) * 9 + tp];
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            const int chunk = (c >> 3) ^ (o & 7);
+            const size_t pos = ((size_t)tp * 64 + o) * 64 + chunk * 8 + (c & 7);
+            img[pos] = hi;
+            img[(size_t)9 * 64 * 64 + pos] = lo;
+          }
+      __half* dh = nullptr;
+      PDS_TRY(dev_alloc(h, &dh, img.size()));
+      PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      L.w_mid_tc = dh;
+    }
+  }
+  // activation buffers
+  const size_t px = (size_t)h->d.hw;
+  int chunk = h->cfg.denoiser_chunk;
+  if (chunk <= 0) {
+    const size_t target_px = (size_t)8 << 20;   // 8 Mpx per pass = 2 GiB per activation buffer
+    chunk = (int)std::max<size_t>(1, target_px / px);
+  }
+  chunk = std::min(chunk, h->d.B);
+  h->chunk = chunk;
+  const size_t act_elems = (size_t)chunk * 2 * px * 64;
+  PDS_TRY(dev_alloc(h, &h->act[0], act_elems));
+  PDS_TRY(dev_alloc(h, &h->act[1], act_elems));
+  if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+    PDS_TRY(tc_plan_create(chunk, h->d.H, h->d.W, h->act[0], h->act[1], &h->tc));
+  }
+  h->have_net = true;
+  return 0;
+}
+
+int pds_phi(pds_handle_t h, const float* in, float* out, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  return apply_phi(h, false, in, out, (cudaStream_t)stream);
+}
+
+int pds_phi_adj(pds_handle_t h, const float* in, float* out, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  return apply_phi(h, true, in, out, (cudaStream_t)stream);
+}
+
+int pds_proj_l2_ball(pds_handle_t h, const float* x, const float* c, float eps, float* out, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  cudaStream_t st = (cudaStream_t)stream;
+  PDS_CUDA_OK(cudaMemsetAsync(h->scratch, 0, (size_t)h->d.B * sizeof(double), st));
+  PDS_LAUNCH(h, launch_diff_norm2(h->d, x, c, h->scratch, st));
+  PDS_LAUNCH(h, launch_proj_l2_apply(h->d, x, c, eps, h->scratch, out, st));
+  return 0;
+}
+
+int pds_proj_l1_ball(pds_handle_t h, const float* x, float eta, float* out, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(x != out, "proj_l1_ball cannot run in place");
+  PDS_REQUIRE(eta >= 0.f, "eta must be >= 0");
+  PDS_LAUNCH(h, launch_l1ball(h->d, x, nullptr, h->prm, nullptr, eta, out, nullptr, (cudaStream_t)stream));
+  return 0;
+}
+
+int pds_prox_gkl(pds_handle_t h, const float* x, const float* x0, float gamma, float alpha, float* out, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_LAUNCH(h, launch_prox_gkl(h->d, x, x0, gamma, alpha, out, (cudaStream_t)stream));
+  return 0;
+}
+
+int pds_dncnn_forward(pds_handle_t h, const float* in, float* out, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(in != out, "dncnn_forward cannot run in place");
+  return run_dncnn(h, in, out, (cudaStream_t)stream);
+}
+
+int pds_set_problem(pds_handle_t h, const float* x0, const float* obs, const float* xtrue, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(x0 && obs, "x0 and obs are required");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = total_elems(h) * sizeof(float);
+  h->cur = h->scur = h->iter = 0;
+  PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0], x0, nb, cudaMemcpyDeviceToDevice, st));
+  PDS_CUDA_OK(cudaMemcpyAsync(h->obs, obs, nb, cudaMemcpyDeviceToDevice, st));
+  h->have_true = xtrue != nullptr;
+  if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyDeviceToDevice, st));
+  PDS_CUDA_OK(cudaMemsetAsync(h->t, 0, nb, st));
+  if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
+  PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
+  h->have_problem = true;
+  return 0;
+}
+
+int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(h->have_problem, "pds_set_problem has not been called");
+  PDS_REQUIRE(h->have_params, "pds_set_item_params has not been called");
+  PDS_REQUIRE(n_iter >= 0 && h->iter + n_iter <= h->cfg.max_iter, "n_iter exceeds the max_iter the handle was created with");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n_iter; ++i) {
+    if (h->cfg.method <= PDS_METHOD_C) PDS_TRY(pds_iteration(h, st));
+    else PDS_TRY(fbs_red_iteration(h, st));
+  }
+  return 0;
+}
+
+int pds_iterations_done(pds_handle_t h) { return h ? h->iter : -1; }
+
+int pds_get_state(pds_handle_t h, float* x, float* s, float* y, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(h->have_problem, "no problem set");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = total_elems(h) * sizeof(float);
+  if (x) PDS_CUDA_OK(cudaMemcpyAsync(x, h->xbuf[h->cur], nb, cudaMemcpyDeviceToDevice, st));
+  if (s) {
+    if (h->sbuf[0]) PDS_CUDA_OK(cudaMemcpyAsync(s, h->sbuf[h->scur], nb, cudaMemcpyDeviceToDevice, st));
+    else PDS_CUDA_OK(cudaMemsetAsync(s, 0, nb, st));
+  }
+  if (y) {
+    const size_t row = (size_t)h->d.B * NSUM;
+    const double* sums = h->iter > 0 ? h->sums + (size_t)(h->iter - 1) * row : nullptr;
+    PDS_LAUNCH(h, launch_scale_by_sigma(h->d, h->t, h->prm, sums, h->cfg.method, y, st));
+  }
+  return 0;
+}
+
+int pds_get_traces(pds_handle_t h, double* trace_host, size_t cap, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  const size_t n = (size_t)h->iter * h->d.B * NSUM;
+  PDS_REQUIRE(trace_host && cap >= n, "trace buffer too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  PDS_CUDA_OK(cudaMemcpyAsync(trace_host, h->sums, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  PDS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const float* xtrue, int n_iter, float* x_out, float* s_out,
+                     double* trace_host, size_t trace_cap, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(x0 && obs && x_out, "x0, obs and x_out are required");
+  PDS_REQUIRE(n_iter >= 0 && n_iter <= h->cfg.max_iter, "n_iter exceeds max_iter");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t nb = total_elems(h) * sizeof(float);
+  h->cur = h->scur = h->iter = 0;
+  PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0], x0, nb, cudaMemcpyHostToDevice, st));
+  PDS_CUDA_OK(cudaMemcpyAsync(h->obs, obs, nb, cudaMemcpyHostToDevice, st));
+  h->have_true = xtrue != nullptr;
+  if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyHostToDevice, st));
+  PDS_CUDA_OK(cudaMemsetAsync(h->t, 0, nb, st));
+  if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
+  PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
+  h->have_problem = true;
+  PDS_TRY(pds_run(h, n_iter, stream));
+  PDS_CUDA_OK(cudaMemcpyAsync(x_out, h->xbuf[h->cur], nb, cudaMemcpyDeviceToHost, st));
+  if (s_out) {
+    if (h->sbuf[0]) PDS_CUDA_OK(cudaMemcpyAsync(s_out, h->sbuf[h->scur], nb, cudaMemcpyDeviceToHost, st));
+    else std::memset(s_out, 0, nb);
+  }
+  if (trace_host) {
+    const size_t n = (size_t)h->iter * h->d.B * NSUM;
+    PDS_REQUIRE(trace_cap >= n, "trace buffer too small");
+    PDS_CUDA_OK(cudaMemcpyAsync(trace_host, h->sums, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  PDS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+long long pds_kernel_launches(pds_handle_t h) { return h ? h->launches : -1; }
+size_t pds_workspace_bytes(pds_handle_t h) { return h ? h->bytes : 0; }
+
+/* test hook: select the tcgen05 descriptor variant (see dncnn_tc.cu) */
+int pds_debug_set_tc_variant(pds_handle_t h, int variant) {
+  if (!h) return 1;
+  h->tc_variant = variant;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+"""The PnP-PDS iteration with the reference's entry point (iteration.py:10-196), resident on one B200.
+
+test_iter(...) keeps the reference's 21-argument signature and 6-tuple result; run_batch(...) is the
+batched form (B independent restorations, per-item hyper-parameters) that the drivers and the
+multi-GPU sharding use.  The loop itself is pds_run / pds_restore_host in libpnp_pds.so.
+"""
+from __future__ import annotations
+
+import time
+from typing import Sequence
+
+import numpy as np
+
+from .engine import RESIDENT_METHODS, Engine, canonical_method, l1_ball_radius, l2_ball_radius, metrics_from_traces
+from .models.weights import DnCNNWeights, load_weights
+from .operators import ObservationOperator, sampling_mask
+from .utils.utils_eval import eval_ssim
+
+_OUT_OF_SCOPE = {
+    "A-PnPPDS-BM3D", "A-PnPFBS-BM3D", "comparisonB-1", "C-PnPPDS-BM3D",      # need the bm3d wheel (CPU-only algorithm)
+    "A-PDS-TV", "A-FBS-TV", "comparisonB-3",                                   # TV baselines, no denoiser
+}
+_NOT_RESIDENT_YET = {"comparisonB-2", "C-PnPADMM-DnCNN", "C-RED-DnCNN"}     # ADMM cross-checks
+
+
+def _check_ops(phi, adj_phi):
+    if not isinstance(phi, ObservationOperator) or not isinstance(adj_phi, ObservationOperator):
+        raise TypeError("phi/adj_phi must come from pnp_pds_b200.operators.get_observation_operators "
+                        "(arbitrary Python callables would need a CPU path, which does not exist)")
+    if phi.kind != adj_phi.kind or phi.adjoint or not adj_phi.adjoint:
+        raise ValueError("phi/adj_phi are not a matching (phi, adj_phi) pair")
+    if phi.kind not in ("blur", "random_sampling", "Id"):
+        raise ValueError(f"unknown deg_op {phi.kind!r}")
+    return phi.kind
+
+
+def item_params(method_id: str, n: int, gamma1, gamma2, alpha_s, alpha_n, myLambda, gaussian_nl, sp_nl, poisson_alpha, r):
+    """Hyper-parameters as the kernels consume them.  Quirk Q1: A-Proposed never passes r
+    to proj_l2_ball (iteration.py:52) so epsilon uses r = 1; B-Proposed passes r to both projections
+    (iteration.py:56,58)."""
+    r_l2 = r if method_id == "B" else 1.0
+    return dict(gamma1=gamma1, gamma2=gamma2, epsilon=l2_ball_radius(n, alpha_n, gaussian_nl, sp_nl, r_l2),
+                eta=l1_ball_radius(n, alpha_s, sp_nl, r), lam=myLambda, alpha=poisson_alpha)
+
+
+def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict, path_prox, max_iter: int,
+              method: str = "A-Proposed", ch: int = 3, conv_engine: str = "tcgen05", device=None, ssim: str = "final",
+              denoiser_chunk: int = 0):
+    """B restorations at once.  x_0, x_obsrv, x_true: (B,H,W) for ch=1 or (B,3,H,W).
+    params: dict(s) with gamma1, gamma2, alpha_s, alpha_n, myLambda, gaussian_nl, sp_nl, poisson_alpha, r.
+    Returns dict(x, s, c, psnr, ssim, time_per_iter, traces, launches)."""
+    name = canonical_method(method)
+    if name in _OUT_OF_SCOPE:
+        raise ValueError(f"method {method!r} is outside the B200 hot path (BM3D / TV baselines, see DESIGN.md)")
+    if name in _NOT_RESIDENT_YET:
+        raise NotImplementedError(f"method {method!r}: ADMM cross-check loops are not resident yet (DESIGN.md, next rows)")
+    if name not in RESIDENT_METHODS:
+        raise ValueError(f"Unknown method: {method}")
+    mid = RESIDENT_METHODS[name]
+    kind = _check_ops(phi, adj_phi)
+    x_0 = np.asarray(x_0)
+    B = x_0.shape[0]
+    H, W = x_0.shape[-2:]
+    C = 1 if x_0.ndim == 3 else x_0.shape[1]
+    if C != ch:
+        raise ValueError(f"ch={ch} but the images have {C} channels")
+    n = C * H * W
+    weights = path_prox if isinstance(path_prox, DnCNNWeights) else load_weights(str(path_prox))
+    if "unstable" in name:
+        nb = 20 if ch == 3 else 17                                   # iteration.py:34-39
+        if weights.depth != nb or weights.residual_sign > 0:
+            raise RuntimeError(f"'{name}' expects a KAIR DnCNN checkpoint with nb={nb}")
+    plist = [params] * B if isinstance(params, dict) else list(params)
+    if len(plist) != B:
+        raise ValueError("need one parameter dict per item")
+    items = [item_params(mid, n, p["gamma1"], p["gamma2"], p.get("alpha_s", 1), p.get("alpha_n", 1), p.get("myLambda", 1),
+                         p.get("gaussian_nl", 0), p.get("sp_nl", 0), p.get("poisson_alpha", 300), p.get("r", phi.r if kind == "random_sampling" else 1))
+             for p in plist]
+    eng = Engine(B, C, H, W, method=mid, deg_op=kind, max_iter=max(1, int(max_iter)), conv_engine=conv_engine, device=device,
+                 denoiser_chunk=denoiser_chunk)
+    try:
+        if kind == "blur":
+            eng.set_blur_kernel(phi.h)
+        elif kind == "random_sampling":
+            eng.set_mask(sampling_mask(H, W, phi.r))
+        eng.set_params(items)
+        eng.load_dncnn(weights)
+        import torch
+        t0 = time.perf_counter()
+        x, s, tr = eng.restore_host(x_0, x_obsrv, x_true, int(max_iter), want_s=True)
+        torch.cuda.synchronize(eng.device)
+        wall = time.perf_counter() - t0
+        launches = eng.kernel_launches
+    finally:
+        eng.close()
+    c, psnr = metrics_from_traces(tr, n)                              # [it, B]
+    x = x.reshape(x_0.shape)
+    s = s.reshape(x_0.shape)
+    ssim_data = np.full((int(max_iter), B), np.nan)
+    if ssim != "none" and x_true is not None and max_iter > 0:
+        xt = np.asarray(x_true)
+        for b in range(B):
+            ssim_data[-1, b] = eval_ssim(xt[b], x[b])
+    return dict(x=x, s=s, c=c, psnr=psnr, ssim=ssim_data, time_per_iter=wall / max(1, int(max_iter)), traces=tr,
+                launches=launches)
+
+
+def test_iter(x_0, x_obsrv, x_true, phi, adj_phi, gamma1, gamma2, alpha_s, alpha_n, myLambda, m1, m2, gammaInADMMStep1,
+              gaussian_nl, sp_nl, poisson_alpha, path_prox, max_iter, method="A-Proposed", ch=3, r=1):
+    """Same arguments (and argument order: ..., gamma2, alpha_s, alpha_n, ...) and result tuple as the
+    reference (iteration.py:10,196): (x_n, s_n + 0.5, c, psnr_data, ssim_data, average_time).
+
+    Differences, by design: x_n is float32 (as the reference's denoiser output is); ssim_data holds
+    the final SSIM in its last entry and NaN before it (per-iteration SSIM would force a device->host
+    copy every iteration; pass through run_batch(ssim=...) to change); average_time is wall seconds
+    per iteration including the H2D/D2H copies, not process CPU seconds; an unknown method raises
+    ValueError instead of printing and crashing on an unbound variable (iteration.py:183-185)."""
+    p = dict(gamma1=gamma1, gamma2=gamma2, alpha_s=alpha_s, alpha_n=alpha_n, myLambda=myLambda, gaussian_nl=gaussian_nl,
+             sp_nl=sp_nl, poisson_alpha=poisson_alpha, r=r)
+    x_0 = np.asarray(x_0)
+    res = run_batch(x_0[None], np.asarray(x_obsrv)[None], None if x_true is None else np.asarray(x_true)[None], phi, adj_phi,
+                    p, path_prox, max_iter, method, ch)
+    return (res["x"][0], res["s"][0].astype(np.float64) + 0.5, res["c"][:, 0], res["psnr"][:, 0], res["ssim"][:, 0],
+            res["time_per_iter"])
+
+
+test_iter.__test__ = False  # not a pytest test
