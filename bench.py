@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — PDS megapixel-iterations/s on the BASELINE.json workload, one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      the reference's CPU path (oracle port) on host cores
+
+A "step" is one PnP-PDS iteration (Phi^T + primal, 20-layer DnCNN, Phi + dual prox, metrics) over the
+resident batch.  Workload `cfg4` (BASELINE.json configs[3], the largest single-GPU configuration and
+the one the metric "DnCNN+blur" is quoted on): ours-A, deg_op=blur (blur_1), gaussian_nl=0.01, colour
+DnCNN_nobn_nch_3_nlev_0.01, 64 RGB 1024x1024 images per GPU (weak scaling: every rank restores its own
+64 images, no data-path collective; traces are all-gathered once after the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+METRIC = "PDS megapixel-iterations/sec (DnCNN+blur)"
+UNIT = "Mpx*it/s"
+
+WORKLOADS = {
+    # name: method, deg_op, C, H, W, batch per GPU, arch, params
+    "cfg4": dict(method="ours-A", deg_op="blur", C=3, H=1024, W=1024, batch=64, arch="DnCNN_nobn_nch_3_nlev_0.01",
+                 prm=dict(gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.0,
+                          poisson_alpha=300, r=1.0), poisson=False),
+    "cfg1": dict(method="ours-A", deg_op="blur", C=1, H=256, W=256, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
+                 prm=dict(gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.0,
+                          poisson_alpha=300, r=1.0), poisson=False),
+    "cfg2": dict(method="ours-B", deg_op="random_sampling", C=1, H=512, W=512, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
+                 prm=dict(gamma1=1.0, gamma2=0.49, alpha_n=0.9, alpha_s=0.9, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.1,
+                          poisson_alpha=300, r=0.8), poisson=False),
+    "cfg3": dict(method="ours-C", deg_op="blur", C=1, H=256, W=256, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
+                 prm=dict(gamma1=0.0006, gamma2=1 / 0.0006, alpha_n=0.9, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.0, sp_nl=0.0,
+                          poisson_alpha=100, r=1.0), poisson=True),
+}
+DNCNN_FLOP_PER_PX_MID_LAYER = 2 * 9 * 64 * 64          # one 64->64 3x3 layer (18 of these per denoiser call)
+
+
+def synthetic_image(b, C, H, W):
+    """Frozen synthetic image of SURVEY §8d (same formula as the oracle's; re-stated here because the
+    measured arm may not import oracle/)."""
+    v, u = np.meshgrid(np.arange(W) / W, np.arange(H) / H)
+    base = 0.5 + 0.3 * np.sin(2 * np.pi * 2 * u) * np.cos(2 * np.pi * 3 * v)
+    rng = np.random.default_rng(seed=b)
+    img = np.stack([np.clip(base + 0.05 * c + 0.1 * (rng.random((H, W)) - 0.5), 0.05, 0.95) for c in range(C)]).astype(np.float32)
+    return img[0] if C == 1 else img
+
+
+def load_assets():
+    return np.load(os.path.join(GOLDEN, "assets.npz"))["blur_1"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tensor_burst=d["bf16_tflops"], tensor=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) == bit and bin(bit).count("1") == 1:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        r = sorted(x for x in self.reasons if x not in ("None", "GpuIdle", "All"))
+        pretty = {"SwPowerCap": "sw_power_cap", "HwSlowdown": "hw_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                  "SwThermalSlowdown": "sw_thermal_slowdown", "HwPowerBrakeSlowdown": "hw_power_brake_slowdown",
+                  "ApplicationsClocksSetting": "applications_clocks_setting", "SyncBoost": "sync_boost",
+                  "DisplayClockSetting": "display_clock_setting"}
+        return dict(sm_mhz=float(np.median(self.sm)) if self.sm else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted({pretty.get(x, x) for x in r}))
+
+
+def cpu_iteration_setup(wl, H, W):
+    """Oracle-port state for one image of the workload cropped to (H, W): returns a closure doing ONE iteration."""
+    from oracle import pds_oracle as O
+    from pnp_pds_b200.models.weights import load_weights          # pure file parsing, no GPU
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    h = load_assets()
+    w = load_weights(os.path.join(GOLDEN, "weights", wl["arch"] + ".pdsw"))
+    prm = wl["prm"]
+    img = O.synthetic_image(0, wl["C"], H, W)
+    phi, adj = O.make_operators(wl["deg_op"], h, prm["r"], fft=True)
+    x0, obs = O.synthesize_observation(img, wl["deg_op"], h, prm["r"], prm["gaussian_nl"], prm["sp_nl"], wl["poisson"],
+                                       prm["poisson_alpha"])
+    den = lambda z: O.dncnn_forward_torch(w.layers, z, w.slope, w.residual_sign, w.clamp)
+    state = dict(x=x0, y=np.zeros(x0.shape), s=np.zeros(x0.shape))
+    method = O.METHOD_ALIASES.get(wl["method"], wl["method"])
+
+    def one_iteration():
+        # one trip of oracle.pds_iterations, state carried across calls
+        st = state
+        x, _, c, psnr, snaps = O.pds_iterations(st["x"], obs, img, phi, adj, den, prm["gamma1"], prm["gamma2"], prm["alpha_s"],
+                                                prm["alpha_n"], prm["myLambda"], prm["gaussian_nl"], prm["sp_nl"], prm["poisson_alpha"],
+                                                1, method, prm["r"], snapshots=(1,), y0=st["y"], s0=st["s"])
+        st["x"], st["y"], st["s"] = snaps[1]["x"], snaps[1]["y"], snaps[1]["s"]
+        return float(psnr[-1])
+
+    return one_iteration
+
+
+def cpu_baseline(wl, budget_s=25.0):
+    """Bounded sample of the workload on the host cores: one image, one iteration per step, largest size whose
+    iteration fits the budget.  Returns the dict for the JSON line."""
+    import torch
+    H, W = wl["H"], wl["W"]
+    t0 = time.perf_counter()
+    it = cpu_iteration_setup(wl, min(H, 256), min(W, 256))
+    it()
+    t = time.perf_counter()
+    it()
+    per_px = (time.perf_counter() - t) / (min(H, 256) * min(W, 256))
+    size = (H, W)
+    while size[0] * size[1] * per_px * 2 > budget_s and size[0] > 256:
+        size = (size[0] // 2, size[1] // 2)
+    it = cpu_iteration_setup(wl, *size)
+    it()                                       # warm-up
+    t = time.perf_counter()
+    n = 0
+    while n < 1 or (time.perf_counter() - t < budget_s / 3 and n < 5):
+        it()
+        n += 1
+    dt = (time.perf_counter() - t) / n
+    return dict(value=size[0] * size[1] / dt / 1e6, unit=UNIT, cores=torch.get_num_threads(), kind="port",
+                sample=f"1 image {wl['C']}x{size[0]}x{size[1]} of the workload, {n} timed iteration(s) after 1 warm-up, "
+                       f"oracle port (numpy FFT blur + torch CPU conv2d, {torch.get_num_threads()} threads), "
+                       f"os.cpu_count()={os.cpu_count()}")
+
+
+def run_reference_arm(a, wl):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import torch
+    H, W = wl["H"], wl["W"]
+    it = cpu_iteration_setup(wl, 256, 256)
+    it()
+    t = time.perf_counter()
+    it()
+    per_px = (time.perf_counter() - t) / (256 * 256)
+    size = (H, W)
+    total = a.steps + a.warmup
+    while size[0] * size[1] * per_px * total > 150.0 and size[0] > 128:
+        size = (size[0] // 2, size[1] // 2)
+    it = cpu_iteration_setup(wl, *size)
+    for _ in range(a.warmup):
+        it()
+    t = time.perf_counter()
+    for _ in range(a.steps):
+        it()
+    dt = time.perf_counter() - t
+    val = size[0] * size[1] * a.steps / dt / 1e6
+    sample = (f"1 image {wl['C']}x{size[0]}x{size[1]} per step (bounded sample of {a.workload}), oracle port of the reference CPU path "
+              f"(numpy FFT blur + torch CPU conv2d), {torch.get_num_threads()} threads")
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=a.gpus, steps=a.steps, warmup=a.warmup,
+                ms_per_step=dt / a.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32/f64",
+                data="synthetic", config=dict(workload=a.workload, method=wl["method"], deg_op=wl["deg_op"], arch=wl["arch"]),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=torch.get_num_threads(), kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
+    ap.add_argument("--engine", default="tcgen05", choices=["tcgen05", "simt"])
+    ap.add_argument("--chunk", type=int, default=0, help="images per denoiser pass (0 = library default)")
+    ap.add_argument("--e2e-iters", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    wl = dict(WORKLOADS[a.workload])
+    if a.batch:
+        wl["batch"] = a.batch
+    if a.impl == "reference":
+        return run_reference_arm(a, wl)
+
+    import torch
+    from pnp_pds_b200 import main as pmain
+    from pnp_pds_b200 import operators
+    from pnp_pds_b200.engine import RESIDENT_METHODS, Engine, canonical_method, metrics_from_traces
+    from pnp_pds_b200.iteration import item_params
+    from pnp_pds_b200.models.weights import load_weights
+    from pnp_pds_b200.parallel import gather_rows, init_distributed
+
+    rank, local_rank, world = init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    B, C, H, W = wl["batch"], wl["C"], wl["H"], wl["W"]
+    n = C * H * W
+    prm = wl["prm"]
+    mid = RESIDENT_METHODS[canonical_method(wl["method"])]
+    hker = load_assets()
+    weights = load_weights(os.path.join(GOLDEN, "weights", wl["arch"] + ".pdsw"))
+
+    # ---- synthetic inputs (host, pinned).  8 distinct images, repeated to the batch; the observation is
+    # synthesised with the product's own operator + the reference-order noise functions (seed 1234).
+    phi, adj = operators.get_observation_operators(wl["deg_op"], hker, prm["r"])
+    n_distinct = min(B, 8)
+    trues, x0s, obss = [], [], []
+    for b in range(n_distinct):
+        img = synthetic_image(rank * 1000 + b, C, H, W)
+        x0, obs = pmain.synthesize_observation(img, phi, wl["deg_op"], prm["gaussian_nl"], prm["sp_nl"], wl["poisson"], prm["poisson_alpha"])
+        trues.append(img); x0s.append(x0); obss.append(obs)
+    shape = (B, C, H, W)
+    pin = lambda: torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    h_true, h_x0, h_obs, h_out = pin(), pin(), pin(), pin()
+    for b in range(B):
+        h_true[b] = torch.from_numpy(np.asarray(trues[b % n_distinct], dtype=np.float32).reshape(C, H, W))
+        h_x0[b] = torch.from_numpy(np.asarray(x0s[b % n_distinct], dtype=np.float32).reshape(C, H, W))
+        h_obs[b] = torch.from_numpy(np.asarray(obss[b % n_distinct], dtype=np.float32).reshape(C, H, W))
+
+    max_iter = a.warmup + a.steps + 2 * a.e2e_iters + 4
+    eng = Engine(B, C, H, W, method=mid, deg_op=wl["deg_op"], max_iter=max_iter, conv_engine=a.engine, device=local_rank,
+                 denoiser_chunk=a.chunk)
+    if wl["deg_op"] == "blur":
+        eng.set_blur_kernel(hker)
+    elif wl["deg_op"] == "random_sampling":
+        eng.set_mask(operators.sampling_mask(H, W, prm["r"]))
+    eng.set_params(item_params(mid, n, prm["gamma1"], prm["gamma2"], prm["alpha_s"], prm["alpha_n"], prm["myLambda"], prm["gaussian_nl"],
+                               prm["sp_nl"], prm["poisson_alpha"], prm["r"]))
+    eng.load_dncnn(weights)
+
+    # ---- device-resident timing: inputs already in HBM when the timed region starts
+    eng.set_problem(h_x0.to(dev, non_blocking=True), h_obs.to(dev, non_blocking=True), h_true.to(dev, non_blocking=True))
+    for _ in range(a.warmup):
+        eng.run(1)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.profile(True)
+    launches0 = eng.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    e0.record()
+    for _ in range(a.steps):
+        eng.run(1)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        torch.distributed.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.kernel_launches - launches0
+    prof = eng.profile_read(reset=True)
+    eng.profile(False)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    px_per_step = B * H * W * world
+    value = px_per_step * a.steps / (ms_max * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI call (H2D of x0/obs/x_true + loop + D2H of x and traces)
+    def e2e_call(n_it):
+        t = time.perf_counter()
+        x, s, tr = eng.restore_host(h_x0.numpy(), h_obs.numpy(), h_true.numpy(), n_it, want_s=False)
+        torch.cuda.synchronize(dev)
+        return time.perf_counter() - t, tr
+    e2e_call(1)
+    if world > 1:
+        torch.distributed.barrier()
+    dt_e2e, tr = e2e_call(a.e2e_iters)
+    t_e = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t_e, op=torch.distributed.ReduceOp.MAX)
+    e2e_value = px_per_step * a.e2e_iters / float(t_e.item()) / 1e6
+    nbytes = B * n * 4
+    c_tr, psnr_tr = metrics_from_traces(tr, n)
+    # the one collective of the path: gather per-item final PSNR / c across ranks (NCCL all-gather)
+    rows = np.stack([psnr_tr[-1], c_tr[-1]], axis=1)
+    allrows = gather_rows(rows, B * world) if world > 1 else rows
+
+    if rank == 0:
+        pk = peaks()
+        mid_ms, mid_n = prof["conv_mid"]
+        chunk = min(B, a.chunk or max(1, (8 << 20) // (H * W)))
+        n_mid_layers = weights.depth - 2
+        total_flop = DNCNN_FLOP_PER_PX_MID_LAYER * float(B * H * W) * n_mid_layers * a.steps
+        achieved = total_flop / (mid_ms * 1e-3) / 1e12 if mid_n else None
+        dual_ms, dual_n = prof["dual"]
+        prim_ms, prim_n = prof["primal"]
+        elem_bytes = (20 + 4) * n * B       # dual: read x+, x, t, b, x_true, write t (20 B + 4 B with PSNR)
+        prim_bytes = 12 * n * B
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms_max / a.steps,
+            higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32 state; DnCNN body fp16 hi/lo split operands with fp32 accumulation" if a.engine == "tcgen05" else "f32",
+            data="synthetic",
+            config=dict(workload=a.workload, method=wl["method"], deg_op=wl["deg_op"], arch=wl["arch"], batch_per_gpu=B,
+                        shape=[C, H, W], conv_engine=a.engine, denoiser_chunk_images=int(chunk),
+                        l2="inputs larger than L2 (state arrays %.0f MiB each, activations %.0f MiB per pass)" % (nbytes / 2**20, chunk * H * W * 256 / 2**20),
+                        parallelism=f"independent images sharded over {world} rank(s), no data-path collective"),
+            gpu_launches=int(launches),
+            clocks=sampler.result(),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=3 * nbytes, d2h_bytes_per_step=nbytes + a.e2e_iters * B * 4 * 8,
+                     iterations_per_call=a.e2e_iters, api="pds_restore_host (host buffers in, host buffers out)"),
+            roofline=dict(bound="tensor", kernel="conv_mid_tc_kernel" if a.engine == "tcgen05" else "conv_mid_simt_kernel",
+                          achieved=achieved, peak=pk["tensor"], unit="TFLOP/s", frac=(achieved / pk["tensor"]) if achieved else None,
+                          traffic=None, peak_source=pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                          launches=int(mid_n), avg_ms=mid_ms / max(1, mid_n),
+                          share_of_step=mid_ms / ms if ms else None,
+                          note="algorithmic FLOPs = 73728 per pixel per layer; the fp16 hi/lo split issues 3 MMAs per algorithmic MAC"),
+            roofline_hbm=dict(bound="hbm", kernel="dual (fused Phi + dual prox + metrics)", achieved=elem_bytes / (dual_ms / max(1, dual_n) * 1e-3) / 1e9 if dual_n else None,
+                              peak=pk["hbm"], unit="GB/s",
+                              frac=(elem_bytes / (dual_ms / max(1, dual_n) * 1e-3) / 1e9 / pk["hbm"]) if dual_n else None,
+                              primal_achieved=prim_bytes / (prim_ms / max(1, prim_n) * 1e-3) / 1e9 if prim_n else None),
+            kernel_ms={k: dict(ms=v[0], launches=v[1]) for k, v in prof.items()},
+            quality=dict(final_psnr_mean=float(np.mean(allrows[:, 0])), c_last_mean=float(np.mean(allrows[:, 1])),
+                         iterations=a.e2e_iters),
+        )
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(wl)
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -136,6 +136,13 @@ int pds_restore_host(pds_handle_t h, const float* x0_host, const float* obs_host
                      size_t trace_capacity_doubles, pds_stream_t stream);
 
 /* ---- introspection for tests / bench ---- */
+/* per-kernel device timing: when enabled, every launch of the categories below is bracketed by CUDA
+ * events on the launching stream; pds_profile_read synchronises the stream and returns accumulated
+ * milliseconds and launch counts per category (arrays of PDS_PROF_NCAT). */
+enum { PDS_PROF_PRIMAL = 0, PDS_PROF_DUAL = 1, PDS_PROF_L1BALL = 2, PDS_PROF_CONV_FIRST = 3, PDS_PROF_CONV_MID = 4,
+       PDS_PROF_CONV_LAST = 5, PDS_PROF_NCAT = 6 };
+int pds_profile_enable(pds_handle_t h, int on);
+int pds_profile_read(pds_handle_t h, double* ms_out, long long* count_out, int reset, pds_stream_t stream);
 /* kernels launched by this handle since creation */
 long long pds_kernel_launches(pds_handle_t h);
 /* bytes of device workspace owned by the handle */

@@ -68,6 +68,24 @@ def blur_phi_adj(x: np.ndarray, h: np.ndarray) -> np.ndarray:
     return _stencil_periodic(x, blur_taps(h, adjoint=True))
 
 
+def _blur_fft(x: np.ndarray, h: np.ndarray, adjoint: bool) -> np.ndarray:
+    """Same periodic operator evaluated with an image-sized real FFT (used by the timed CPU baseline:
+    the reference also works in the Fourier domain, operators.py:13-14).  Equal to the stencil form to
+    round-off (checked in tests/test_oracle_golden.py)."""
+    H, W = x.shape[-2:]
+    l = h.shape[0]
+    c = l // 2
+    k = np.zeros((H, W))
+    for a in range(l):
+        for b in range(l):
+            if h[a, b] != 0.0:
+                k[(a - c) % H, (b - c) % W] += h[a, b]      # periodic convolution kernel centred at c
+    K = np.fft.rfft2(k)
+    if adjoint:
+        K = np.conj(K)
+    return np.fft.irfft2(np.fft.rfft2(x.astype(np.float64), axes=(-2, -1)) * K, s=(H, W), axes=(-2, -1))
+
+
 def sampling_mask(H: int, W: int, r: float) -> np.ndarray:
     """uint8 (H, W) keep-mask of the random_sampling operator (operators.py:40-58).
 
@@ -87,9 +105,11 @@ def sample(x: np.ndarray, mask: np.ndarray) -> np.ndarray:
     return x * mask.astype(x.dtype)
 
 
-def make_operators(deg_op: str, h: np.ndarray | None, r: float, shape_hw=None):
+def make_operators(deg_op: str, h: np.ndarray | None, r: float, shape_hw=None, fft: bool = False):
     """(phi, adj_phi) closures like operators.get_observation_operators (operators.py:60-79)."""
     if deg_op == "blur":
+        if fft:
+            return (lambda x: _blur_fft(x, h, False)), (lambda x: _blur_fft(x, h, True))
         return (lambda x: blur_phi(x, h)), (lambda x: blur_phi_adj(x, h))
     if deg_op == "random_sampling":
         cache = {}
@@ -216,6 +236,31 @@ def dncnn_forward(layers, x: np.ndarray, slope: float = 0.01, residual_sign: flo
     if clamp:
         out = np.clip(out, 0.0, 1.0)
     out = out.astype(np.float32)
+    return out[0] if squeeze else out
+
+
+def dncnn_forward_torch(layers, x: np.ndarray, slope: float = 0.01, residual_sign: float = 1.0,
+                        clamp: bool = True) -> np.ndarray:
+    """Same network through torch's CPU conv2d with all host threads — what the reference itself runs
+    on a CPU-only box (denoiser.py:34-46).  Used for the timed CPU baseline; agrees with
+    dncnn_forward to fp32 summation order."""
+    import torch
+    import torch.nn.functional as F
+    squeeze = x.ndim == 2
+    a = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    a = a[None, None] if squeeze else a[None]
+    with torch.no_grad():
+        if clamp:
+            a = a.clamp(0, 1)
+        x_in = a
+        for i, (w, b) in enumerate(layers):
+            a = F.conv2d(a, torch.from_numpy(w), torch.from_numpy(b), padding=1)
+            if i != len(layers) - 1:
+                a = F.leaky_relu(a, slope)
+        out = a + x_in if residual_sign > 0 else x_in - a
+        if clamp:
+            out = out.clamp(0, 1)
+    out = out[0].numpy()
     return out[0] if squeeze else out
 
 
@@ -362,7 +407,7 @@ METHOD_ALIASES = {
 
 def pds_iterations(x_0, x_obsrv, x_true, phi, adj_phi, denoise, gamma1, gamma2, alpha_s, alpha_n,
                    myLambda, gaussian_nl, sp_nl, poisson_alpha, max_iter, method="A-Proposed", r=1,
-                   m1=15, m2=15, gammaInADMMStep1=0.1, snapshots=()):
+                   m1=15, m2=15, gammaInADMMStep1=0.1, snapshots=(), y0=None, s0=None):
     """Restatement of iteration.test_iter for the DnCNN-based methods.
 
     `denoise` is a callable image->float32 image (the Denoiser.denoise of denoiser.py:14-16).
@@ -371,8 +416,8 @@ def pds_iterations(x_0, x_obsrv, x_true, phi, adj_phi, denoise, gamma1, gamma2, 
     """
     method = METHOD_ALIASES.get(method, method)
     x = x_0
-    y = np.zeros(x_0.shape)
-    s = np.zeros(x_0.shape)
+    y = np.zeros(x_0.shape) if y0 is None else y0      # y0/s0: resume from a previous call (bench CPU baseline)
+    s = np.zeros(x_0.shape) if s0 is None else s0
     z = np.zeros(x_0.shape)
     d = np.zeros(x_0.shape)
     c = np.zeros(max_iter)

@@ -16,6 +16,7 @@ METHODS = {"A": 0, "B": 1, "C": 2, "FBS": 3, "RED": 4}
 DEG_OPS = {"Id": 0, "blur": 1, "random_sampling": 2}
 CONV_ENGINES = {"tcgen05": 0, "simt": 1}
 TRACE_WIDTH = 4
+PROF_CATS = ("primal", "dual", "l1ball", "conv_first", "conv_mid", "conv_last")
 
 
 class PdsConfig(C.Structure):
@@ -55,6 +56,8 @@ def _declare(lib):
         "pds_get_state": (i, [vp, vp, vp, vp, vp]),
         "pds_get_traces": (i, [vp, vp, sz, vp]),
         "pds_restore_host": (i, [vp, vp, vp, vp, i, vp, vp, vp, sz, vp]),
+        "pds_profile_enable": (i, [vp, i]),
+        "pds_profile_read": (i, [vp, vp, vp, i, vp]),
         "pds_kernel_launches": (C.c_longlong, [vp]),
         "pds_workspace_bytes": (sz, [vp]),
         "pds_debug_set_tc_variant": (i, [vp, i]),

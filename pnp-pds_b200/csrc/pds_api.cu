@@ -51,6 +51,14 @@ struct pds_handle_s {
   std::vector<void*> allocs;
   size_t bytes = 0;
   long long launches = 0;
+  // optional per-kernel timing (bench.py roofline): event pairs around the launches of each category
+  bool prof = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  double prof_ms[PDS_PROF_NCAT] = {};
+  long long prof_n[PDS_PROF_NCAT] = {};
 };
 
 namespace {
@@ -77,6 +85,32 @@ int dev_alloc(pds_handle_s* h, T** p, size_t count) {
   do {                        \
     PDS_CUDA_OK(expr);        \
     (h)->launches++;          \
+  } while (0)
+
+cudaEvent_t prof_event(pds_handle_s* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_used++];
+}
+
+// launch + (optionally) bracket with events on the launching stream
+#define PDS_LAUNCH_P(h, cat, st, expr)                         \
+  do {                                                         \
+    cudaEvent_t _ea = nullptr, _eb = nullptr;                  \
+    if ((h)->prof) {                                           \
+      _ea = prof_event(h);                                     \
+      _eb = prof_event(h);                                     \
+      cudaEventRecord(_ea, st);                                \
+    }                                                          \
+    PDS_CUDA_OK(expr);                                         \
+    (h)->launches++;                                           \
+    if ((h)->prof) {                                           \
+      cudaEventRecord(_eb, st);                                \
+      (h)->prof_recs.push_back({cat, _ea, _eb});               \
+    }                                                          \
   } while (0)
 
 int check_handle(pds_handle_t h) {
@@ -113,17 +147,17 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const int nimg = (d.B - b0 < h->chunk) ? d.B - b0 : h->chunk;
     const float* cin = in + (size_t)b0 * d.n;
     float* cout = out + (size_t)b0 * d.n;
-    PDS_LAUNCH(h, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
+    PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
       if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
-        PDS_LAUNCH(h, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
       } else {
-        PDS_LAUNCH(h, launch_conv_mid_simt(nimg, d.H, d.W, h->act[src], h->layers[l], h->slope, h->act[src ^ 1], st));
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_simt(nimg, d.H, d.W, h->act[src], h->layers[l], h->slope, h->act[src ^ 1], st));
       }
       src ^= 1;
     }
-    PDS_LAUNCH(h, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
+    PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
   }
   return 0;
 }
@@ -153,15 +187,15 @@ int pds_iteration(pds_handle_s* h, cudaStream_t st) {
   StepArgs a = step_args(h);
   const bool blur = h->cfg.deg_op == PDS_OP_BLUR;
   // x_{k+1} = D(x_k - gamma1 Phi^T y_k)
-  if (blur) PDS_LAUNCH(h, launch_primal_blur(a, h->taps, st));
-  else PDS_LAUNCH(h, launch_primal_pointwise(a, st));
+  if (blur) PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_blur(a, h->taps, st));
+  else PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_pointwise(a, st));
   // s_{k+1} = P_l1(s_k - gamma1 y_k)
   if (h->cfg.method == PDS_METHOD_B)
-    PDS_LAUNCH(h, launch_l1ball(h->d, a.s_old, h->t, h->prm, a.sums_prev, -1.f, h->sbuf[h->scur ^ 1], nullptr, st));
+    PDS_LAUNCH_P(h, PDS_PROF_L1BALL, st, launch_l1ball(h->d, a.s_old, h->t, h->prm, a.sums_prev, -1.f, h->sbuf[h->scur ^ 1], nullptr, st));
   PDS_TRY(run_dncnn(h, h->u, h->xbuf[h->cur ^ 1], st));
   // y_{k+1}
-  if (blur) PDS_LAUNCH(h, launch_dual_blur(a, h->taps, st));
-  else PDS_LAUNCH(h, launch_dual_pointwise(a, st));
+  if (blur) PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_blur(a, h->taps, st));
+  else PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_pointwise(a, st));
   h->cur ^= 1;
   if (h->cfg.method == PDS_METHOD_B) h->scur ^= 1;
   h->iter++;
@@ -274,6 +308,7 @@ int pds_destroy(pds_handle_t h) {
   if (!h) return 0;
   cudaSetDevice(h->cfg.device);
   if (h->tc) tc_plan_destroy(h->tc);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return 0;
@@ -570,6 +605,31 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
     PDS_CUDA_OK(cudaMemcpyAsync(trace_host, h->sums, n * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   PDS_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pds_profile_enable(pds_handle_t h, int on) {
+  PDS_TRY(check_handle(h));
+  h->prof = on != 0;
+  return 0;
+}
+
+int pds_profile_read(pds_handle_t h, double* ms_out, long long* count_out, int reset, pds_stream_t stream) {
+  PDS_TRY(check_handle(h));
+  PDS_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  for (const auto& r : h->prof_recs) {
+    float ms = 0.f;
+    PDS_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+    h->prof_ms[r.cat] += ms;
+    h->prof_n[r.cat] += 1;
+  }
+  h->prof_recs.clear();
+  h->ev_used = 0;
+  for (int c = 0; c < PDS_PROF_NCAT; ++c) {
+    if (ms_out) ms_out[c] = h->prof_ms[c];
+    if (count_out) count_out[c] = h->prof_n[c];
+    if (reset) { h->prof_ms[c] = 0; h->prof_n[c] = 0; }
+  }
   return 0;
 }
 

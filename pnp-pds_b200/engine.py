@@ -219,6 +219,17 @@ class Engine:
                                              self._stream()))
         return x, s, tr
 
+    def profile(self, on: bool = True):
+        _lib.check(self.lib.pds_profile_enable(self._h, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{category: (milliseconds, launches)} accumulated by CUDA events around each kernel launch."""
+        n = len(_lib.PROF_CATS)
+        ms = (C.c_double * n)()
+        cnt = (C.c_longlong * n)()
+        _lib.check(self.lib.pds_profile_read(self._h, ms, cnt, 1 if reset else 0, self._stream()))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.PROF_CATS)}
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.pds_kernel_launches(self._h))

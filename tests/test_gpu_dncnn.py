@@ -1,0 +1,101 @@
+"""DnCNN forward parity on the B200: both conv engines vs the reference's outputs (golden) and the oracle."""
+import numpy as np
+import pytest
+
+from conftest import weights_path
+from oracle import pds_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIMPLE = ["DnCNN_nobn_nch_1_nlev_0.01", "DnCNN_nobn_nch_3_nlev_0.01", "DnCNN_nobn_nch_1_nlev_0.009"]
+KAIR = [("dncnn_15", 1, 17), ("dncnn_color_blind", 3, 20), ("dncnn3", 1, 20)]
+# fp32 accumulation with activations carried as fp16 hi+lo (2^-22) between 20 layers
+TOL = 1e-5
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("arch", SIMPLE)
+def test_simple_cnn_vs_reference(g_den, arch, engine):
+    from pnp_pds_b200.models.denoiser import Denoiser
+    ch = 3 if "nch_3" in arch else 1
+    den = Denoiser(weights_path(arch), ch, conv_engine=engine)
+    x = g_den[f"{arch}_x"]
+    y = den.denoise(x)
+    ref = g_den[f"{arch}_y"]
+    assert y.dtype == np.float32 and y.shape == ref.shape
+    err = float(np.max(np.abs(y - ref)))
+    print(f"{arch} {engine}: max abs err {err:.3e}")
+    assert err < TOL
+    assert y.min() >= 0 and y.max() <= 1
+
+
+@pytest.mark.parametrize("engine", ["simt", "tcgen05"])
+@pytest.mark.parametrize("arch,ch,nb", KAIR)
+def test_kair_dncnn_vs_reference(g_den, arch, ch, nb, engine):
+    import torch
+    from pnp_pds_b200.models.denoiser import Denoiser
+    from pnp_pds_b200.models.weights import load_weights
+    den = Denoiser(load_weights(weights_path(arch)), ch, conv_engine=engine)
+    x = g_den[f"{arch}_x"]
+    y = den.denoise_batch(x[None])[0]
+    err = float(np.max(np.abs(y - g_den[f"{arch}_y"])))
+    print(f"{arch} {engine}: max abs err {err:.3e}")
+    assert err < 2 * TOL
+
+
+def test_kair_class_interface(g_den):
+    import torch
+    from pnp_pds_b200.models.network_dncnn import DnCNN
+    net = DnCNN(in_nc=1, out_nc=1, nc=64, nb=17, act_mode="R", model_path=weights_path("dncnn_15"))
+    x = torch.from_numpy(g_den["dncnn_15_x"])          # unbatched gray (1,H,W), as iteration.py:108 passes it
+    y = net(x)
+    assert tuple(y.shape) == tuple(x.shape)
+    assert float((y - torch.from_numpy(g_den["dncnn_15_y"])).abs().max()) < 2 * TOL
+    with pytest.raises(RuntimeError):
+        DnCNN(in_nc=1, out_nc=1, nc=64, nb=20, act_mode="R", model_path=weights_path("dncnn_15"))
+
+
+@pytest.mark.parametrize("shape", [(1, 50, 37), (3, 33, 70), (1, 16, 8), (1, 7, 5)])
+def test_engines_agree_ragged_shapes(shape):
+    """Tile edges: H not a multiple of 16, W not a multiple of 8, image smaller than a tile."""
+    from pnp_pds_b200.models.denoiser import Denoiser
+    from pnp_pds_b200.models.weights import load_weights
+    C, H, W = shape
+    arch = SIMPLE[1] if C == 3 else SIMPLE[0]
+    w = load_weights(weights_path(arch))
+    x = np.random.default_rng(5).random(shape).astype(np.float32)
+    ref = O.dncnn_forward(w.layers, x, w.slope, w.residual_sign, w.clamp)
+    for engine in ("simt", "tcgen05"):
+        y = Denoiser(w, C, conv_engine=engine).denoise(x if C == 3 else x[0])
+        err = float(np.max(np.abs(y.reshape(shape) - ref)))
+        print(shape, engine, err)
+        assert err < TOL, (shape, engine)
+
+
+def test_batch_matches_single_and_chunking():
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    w = load_weights(weights_path(SIMPLE[0]))
+    rng = np.random.default_rng(9)
+    x = rng.random((5, 1, 48, 40)).astype(np.float32)
+    outs = []
+    for chunk in (0, 2):                                # default chunk (all 5 at once) and 2 images per pass
+        with Engine(5, 1, 48, 40, conv_engine="tcgen05", denoiser_chunk=chunk) as e:
+            e.load_dncnn(w)
+            outs.append(e.dncnn_forward(e.to_device(x)).cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    with Engine(1, 1, 48, 40, conv_engine="tcgen05") as e:
+        e.load_dncnn(w)
+        for b in range(5):
+            one = e.dncnn_forward(e.to_device(x[b])).cpu().numpy()
+            assert np.array_equal(one[0], outs[0][b])
+
+
+def test_full_size_linearity_free_checks():
+    """256x256 (config 1 size): engines agree with each other; output stays in [0,1]."""
+    from pnp_pds_b200.models.denoiser import Denoiser
+    x = O.synthetic_image(0, 1, 256, 256) + 0.02 * np.random.default_rng(1).standard_normal((256, 256)).astype(np.float32)
+    a = Denoiser(weights_path(SIMPLE[0]), 1, conv_engine="simt").denoise(x)
+    b = Denoiser(weights_path(SIMPLE[0]), 1, conv_engine="tcgen05").denoise(x)
+    assert float(np.max(np.abs(a - b))) < TOL
+    assert a.min() >= 0 and a.max() <= 1

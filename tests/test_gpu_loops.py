@@ -1,0 +1,128 @@
+"""Resident-loop parity on the B200 against traces recorded from the reference (tests/golden/loops.npz,
+long.npz): iterate snapshots, c[i] and PSNR traces; the north-star gates (relative L2 of the final
+iterate <= 1e-4, |dPSNR| <= 0.01 dB after the full iteration count) on the long cases."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import rel_l2, weights_path
+from oracle import pds_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL_L2_GATE = 1e-4       # BASELINE.json north_star
+DPSNR_GATE = 0.01
+
+
+def _run(g, assets, tag, n_iter, engine="tcgen05"):
+    from pnp_pds_b200 import iteration, operators
+    case = json.loads(str(g[f"{tag}/case"]))
+    arch = "DnCNN_nobn_nch_1_nlev_0.01" if case["ch"] == 1 else "DnCNN_nobn_nch_3_nlev_0.01"
+    phi, adj = operators.get_observation_operators(case["deg_op"], assets["blur_1"], case.get("r", 1.0))
+    prm = dict(gamma1=case["gamma1"], gamma2=case["gamma2"], alpha_s=case["alpha_s"], alpha_n=case["alpha_n"],
+               myLambda=case.get("myLambda", 1.0), gaussian_nl=case["gaussian_nl"], sp_nl=case["sp_nl"],
+               poisson_alpha=case.get("poisson_alpha", 300), r=case.get("r", 1.0))
+    res = iteration.run_batch(g[f"{tag}/x0"][None], g[f"{tag}/obs"][None], g[f"{tag}/x_true"][None], phi, adj, prm,
+                              weights_path(arch), n_iter, case["method"], case["ch"], conv_engine=engine)
+    return case, res
+
+
+SHORT = ["A_blur_g", "A_rs_g", "A_id_g", "A_blur_c", "B_rs_g", "B_blur_g", "B_rs_c", "C_blur_g", "C_id_g", "FBS_blur_g", "RED_blur_g"]
+
+
+@pytest.mark.parametrize("engine", ["tcgen05", "simt"])
+@pytest.mark.parametrize("tag", SHORT)
+def test_short_traces(g_loops, assets, tag, engine):
+    case, _ = _run(g_loops, assets, tag, 1, engine)
+    for n in (1, 2, 10, case["iters"]):
+        _, res = _run(g_loops, assets, tag, n, engine)
+        ref_x = g_loops[f"{tag}/x_{n}"]
+        e = rel_l2(res["x"][0], ref_x)
+        print(f"{tag} {engine} n={n}: rel_l2(x)={e:.2e}")
+        assert e < REL_L2_GATE, (tag, n)
+        ref_s = g_loops[f"{tag}/s05_{n}"]
+        assert np.max(np.abs(res["s"][0] + 0.5 - ref_s)) < 1e-4, (tag, n)
+    assert np.allclose(res["c"][:, 0], g_loops[f"{tag}/c"], rtol=5e-3, atol=2e-6), tag
+    assert np.max(np.abs(res["psnr"][:, 0] - g_loops[f"{tag}/psnr"])) < DPSNR_GATE, tag
+
+
+LONG = ["LONG_A_blur_g", "LONG_C_blur_g", "LONG_B_rs_g", "LONG_A_blur_c"]
+
+
+@pytest.mark.parametrize("tag", LONG)
+def test_full_iteration_count_gate(g_long, assets, tag):
+    case, res = _run(g_long, assets, tag, json.loads(str(g_long[f"{tag}/case"]))["iters"])
+    n = case["iters"]
+    e = rel_l2(res["x"][0], g_long[f"{tag}/x_{n}"])
+    dpsnr = abs(res["psnr"][-1, 0] - g_long[f"{tag}/psnr"][-1])
+    print(f"{tag}: {n} iterations, rel_l2={e:.2e}, dPSNR={dpsnr:.2e} dB, c_last={res['c'][-1, 0]:.2e}")
+    assert e <= REL_L2_GATE
+    assert dpsnr <= DPSNR_GATE
+    assert np.max(np.abs(res["psnr"][:, 0] - g_long[f"{tag}/psnr"])) < 5 * DPSNR_GATE
+
+
+def test_test_iter_signature_and_errors(g_loops, assets):
+    from pnp_pds_b200 import iteration, operators
+    tag = "A_blur_g"
+    case = json.loads(str(g_loops[f"{tag}/case"]))
+    phi, adj = operators.get_observation_operators("blur", assets["blur_1"], 1.0)
+    path = weights_path("DnCNN_nobn_nch_1_nlev_0.01")
+    args = (g_loops[f"{tag}/x0"], g_loops[f"{tag}/obs"], g_loops[f"{tag}/x_true"], phi, adj, case["gamma1"], case["gamma2"],
+            case["alpha_s"], case["alpha_n"], 1.0, 15, 15, 0.1, case["gaussian_nl"], case["sp_nl"], 300, path, 10)
+    x, s05, c, psnr, ssim, avg = iteration.test_iter(*args, "ours-A", 1, 1.0)          # legacy alias
+    assert x.dtype == np.float32 and x.shape == (64, 64) and np.all(s05 == 0.5)
+    assert c.shape == psnr.shape == ssim.shape == (10,) and avg > 0
+    assert rel_l2(x, g_loops[f"{tag}/x_10"]) < REL_L2_GATE
+    assert np.isfinite(ssim[-1]) and abs(ssim[-1] - O.eval_ssim(g_loops[f"{tag}/x_true"], x)) < 1e-9
+    with pytest.raises(ValueError):
+        iteration.test_iter(*args, "no-such-method", 1, 1.0)
+    with pytest.raises(ValueError):
+        iteration.test_iter(*args, "A-PnPPDS-BM3D", 1, 1.0)
+    with pytest.raises(TypeError):
+        iteration.test_iter(*args[:3], lambda z: z, lambda z: z, *args[5:], "A-Proposed", 1, 1.0)
+
+
+def test_batched_mixed_parameters_match_single_runs(g_loops, assets):
+    """A batch that mixes grid points (per-item gamma / alpha) reproduces the individual restorations."""
+    from pnp_pds_b200 import iteration, operators
+    tag = "A_blur_g"
+    phi, adj = operators.get_observation_operators("blur", assets["blur_1"], 1.0)
+    path = weights_path("DnCNN_nobn_nch_1_nlev_0.01")
+    base = dict(gamma1=0.99, gamma2=0.99, alpha_s=0.95, alpha_n=0.95, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.0, poisson_alpha=300, r=1.0)
+    grid = [dict(base), dict(base, alpha_n=0.82), dict(base, gamma1=0.5, gamma2=1.5)]
+    x0 = np.stack([g_loops[f"{tag}/x0"]] * 3)
+    obs = np.stack([g_loops[f"{tag}/obs"]] * 3)
+    xt = np.stack([g_loops[f"{tag}/x_true"]] * 3)
+    res = iteration.run_batch(x0, obs, xt, phi, adj, grid, path, 12, "A-Proposed", 1)
+    for k, p in enumerate(grid):
+        one = iteration.run_batch(x0[:1], obs[:1], xt[:1], phi, adj, p, path, 12, "A-Proposed", 1)
+        assert np.array_equal(one["x"][0], res["x"][k]), k
+        assert np.allclose(one["psnr"][:, 0], res["psnr"][:, k], rtol=0, atol=1e-9)
+    assert not np.array_equal(res["x"][0], res["x"][1])
+
+
+@pytest.mark.parametrize("shape,deg_op,method", [((1, 256, 256), "blur", "A-Proposed"), ((1, 512, 512), "random_sampling", "B-Proposed"),
+                                                 ((3, 128, 96), "blur", "A-Proposed")])
+def test_full_size_against_oracle_few_iterations(assets, shape, deg_op, method):
+    """BASELINE config sizes (256^2 ours-A blur, 512^2 ours-B random_sampling): 3 iterations vs the CPU oracle."""
+    from pnp_pds_b200 import iteration, operators
+    from pnp_pds_b200.models.weights import load_weights
+    C, H, W = shape
+    arch = "DnCNN_nobn_nch_1_nlev_0.01" if C == 1 else "DnCNN_nobn_nch_3_nlev_0.01"
+    w = load_weights(weights_path(arch))
+    img = O.synthetic_image(1, C, H, W)
+    sp = 0.1 if method == "B-Proposed" else 0.0
+    r = 0.8 if deg_op == "random_sampling" else 1.0
+    x0, obs = O.synthesize_observation(img, deg_op, assets["blur_1"], r, 0.01, sp, False, 300)
+    prm = dict(gamma1=0.99, gamma2=0.49 if sp else 0.99, alpha_s=0.9, alpha_n=0.9, myLambda=1.0, gaussian_nl=0.01, sp_nl=sp,
+               poisson_alpha=300, r=r)
+    phi, adj = operators.get_observation_operators(deg_op, assets["blur_1"], r)
+    res = iteration.run_batch(x0[None], obs[None], img[None], phi, adj, prm, w, 3, method, C)
+    ophi, oadj = O.make_operators(deg_op, assets["blur_1"], r)
+    den = lambda z: O.dncnn_forward(w.layers, z, w.slope, w.residual_sign, w.clamp)
+    xr, s05, c, psnr, _ = O.pds_iterations(x0, obs, img, ophi, oadj, den, prm["gamma1"], prm["gamma2"], prm["alpha_s"], prm["alpha_n"],
+                                           1.0, 0.01, sp, 300, 3, method, r)
+    assert rel_l2(res["x"][0], xr) < REL_L2_GATE
+    assert np.max(np.abs(res["psnr"][:, 0] - psnr)) < DPSNR_GATE
+    assert np.max(np.abs(res["s"][0] + 0.5 - s05)) < 1e-4

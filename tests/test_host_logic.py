@@ -1,0 +1,196 @@
+"""CPU-only checks of the host side: C-ABI surface, weight conversion, bit-exact masks/noise of the
+product code against the reference's recorded outputs, argument handling, sharding (gloo, world size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, weights_path
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from pnp_pds_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "pnp_pds.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(pds_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in pnp_pds.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert lib.pds_abi_version() == 1
+    assert isinstance(lib.pds_device_count(), int)
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from pnp_pds_b200._lib import PdsError
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200 import operators
+    with pytest.raises(PdsError):
+        Engine(1, 1, 8, 8)
+    phi, _ = operators.get_observation_operators("random_sampling", None, 0.8)
+    with pytest.raises(PdsError):
+        phi(np.ones((8, 8)))
+
+
+def test_product_code_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pnp-pds_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "pds_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_weight_blob_roundtrip_and_shapes():
+    from pnp_pds_b200.models.weights import DnCNNWeights, load_weights
+    for arch, (depth, c, slope, rs, clamp) in {
+        "DnCNN_nobn_nch_1_nlev_0.01": (20, 1, 0.01, 1.0, True), "DnCNN_nobn_nch_3_nlev_0.01": (20, 3, 0.01, 1.0, True),
+        "DnCNN_nobn_nch_1_nlev_0.009": (20, 1, 0.01, 1.0, True), "dncnn_15": (17, 1, 0.0, -1.0, False),
+        "dncnn3": (20, 1, 0.0, -1.0, False), "dncnn_color_blind": (20, 3, 0.0, -1.0, False)}.items():
+        w = load_weights(weights_path(arch))
+        assert (w.depth, w.c_in, w.c_out, w.n_ch, w.residual_sign, w.clamp) == (depth, c, c, 64, rs, clamp)
+        assert abs(w.slope - slope) < 1e-7
+        n_par = sum(a.size + b.size for a, b in w.layers)
+        if depth == 20:
+            assert n_par == (665921 if c == 1 else 668227)
+        w2 = DnCNNWeights.from_blob(w.to_blob())
+        assert all(np.array_equal(a, c_) and np.array_equal(b, d) for (a, b), (c_, d) in zip(w.layers, w2.layers))
+    with pytest.raises(ValueError):
+        DnCNNWeights.from_blob(b"nope" + bytes(60))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/nn"), reason="reference checkpoints not mounted")
+def test_pth_conversion_matches_committed_blobs_and_blocks_foreign_globals(tmp_path):
+    from pnp_pds_b200.models.weights import load_pth
+    for arch in ("DnCNN_nobn_nch_1_nlev_0.01", "dncnn_15"):
+        w = load_pth(f"/root/reference/nn/{arch}.pth")
+        assert w.to_blob() == open(weights_path(arch), "rb").read()
+    import pickle, torch
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    p = tmp_path / "evil.pth"
+    torch.save(Evil(), str(p), _use_new_zipfile_serialization=False)
+    with pytest.raises(pickle.UnpicklingError):
+        load_pth(str(p))
+
+
+@pytest.mark.parametrize("H,W,r", [(32, 32, 0.8), (64, 64, 0.5), (48, 20, 0.7), (256, 256, 0.8), (512, 512, 0.8), (1024, 1024, 0.8)])
+def test_product_mask_bit_exact(g_ops, H, W, r):
+    from pnp_pds_b200.operators import sampling_mask
+    ref = np.unpackbits(g_ops[f"mask_{H}_{W}_{r}"])[: H * W].reshape(H, W)
+    assert np.array_equal(sampling_mask(H, W, r), ref)
+
+
+def test_product_noise_bit_exact(g_noise):
+    from pnp_pds_b200.operators import sampling_mask
+    from pnp_pds_b200.utils import utils_noise as un
+    ident = lambda z: z
+    rs = lambda z: z * sampling_mask(z.shape[-2], z.shape[-1], 0.8)
+    img, imgc = g_noise["img_g"], g_noise["img_c"]
+    assert np.array_equal(un.add_gaussian_noise(img, 0.01, ident), g_noise["gauss_g_id"])
+    assert np.array_equal(un.add_gaussian_noise(rs(img), 0.01, rs), g_noise["gauss_g_rs"])
+    assert np.array_equal(un.apply_poisson_noise(img, 100), g_noise["poisson_g"])
+    assert un.apply_poisson_noise(img, 100).dtype == np.int64
+    assert np.array_equal(un.add_salt_and_pepper_noise(img, 0.1, ident), g_noise["sp_g_id"])
+    assert np.array_equal(un.add_salt_and_pepper_noise(rs(img), 0.1, rs), g_noise["sp_g_rs"])
+    assert np.array_equal(un.add_salt_and_pepper_noise(rs(imgc), 0.1, rs), g_noise["sp_c_rs"])
+    assert np.array_equal(un.add_salt_and_pepper_noise(img, 0.0, ident), g_noise["sp_g_zero"])
+
+
+def test_arg_parsing_defaults_and_aliases():
+    from pnp_pds_b200.engine import canonical_method, RESIDENT_METHODS
+    from pnp_pds_b200.utils.utils_method_master import get_algorithm_denoiser
+    from pnp_pds_b200.utils.utils_parse_args import parse_args_configs, parse_args_exp, parse_args_method
+    from pnp_pds_b200.utils.utils_unparse_args import unparse_args_method
+    assert parse_args_exp({}) == (0, 0, False, 300, "blur", 0.8)                               # utils_parse_args.py:5-10
+    assert parse_args_method({}) == ("ours-A", "DnCNN_nobn_nch_3_nlev_0.01", 10, 1, 1, 1, 1, 1, 15, 15, 0.1)
+    assert parse_args_configs({}) == (3, True, False)
+    assert parse_args_method({"gamma1": 0.5, "m2": 3})[3] == 0.5
+    assert unparse_args_method(*parse_args_method({}))["gammaInADMMStep1"] == 0.1
+    for old, new in (("ours-A", "A-Proposed"), ("ours-B", "B-Proposed"), ("ours-C", "C-Proposed"),
+                     ("comparisonA-1", "A-PnPFBS-DnCNN"), ("comparisonA-6", "A-RED-DnCNN")):
+        assert canonical_method(old) == new and new in RESIDENT_METHODS
+    assert get_algorithm_denoiser("ours-B") == ("PnP-PDS", "DnCNN")
+    assert get_algorithm_denoiser("A-RED-DnCNN") == ("RED-SD", "DnCNN")
+    assert get_algorithm_denoiser("whatever") == ("unknown algorithm", "unknown denoiser")
+
+
+def test_item_params_quirks():
+    from pnp_pds_b200.iteration import item_params
+    n = 512 * 512
+    # B-Proposed passes r to both projections (iteration.py:56,58); cfg2 numbers from SURVEY §8 a-8/a-9
+    pb = item_params("B", n, 1.0, 0.49, 0.9, 0.9, 1, 0.01, 0.1, 300, 0.8)
+    assert abs(pb["epsilon"] - 3.497) < 1e-3 and abs(pb["eta"] - 9437.18) < 0.01
+    # A-Proposed never passes r (iteration.py:52): epsilon uses r = 1 even for random_sampling
+    pa = item_params("A", n, 0.99, 0.99, 0.9, 0.9, 1, 0.01, 0.0, 300, 0.8)
+    assert abs(pa["epsilon"] - np.sqrt(n) * 0.9 * 0.01) < 1e-9
+
+
+def test_metrics_from_traces():
+    from pnp_pds_b200.engine import metrics_from_traces
+    tr = np.zeros((2, 1, 4))
+    tr[:, 0, 1] = [4.0, 1.0]
+    tr[:, 0, 2] = [16.0, 16.0]
+    tr[:, 0, 3] = [0.01 * 100, 0.0001 * 100]
+    c, psnr = metrics_from_traces(tr, 100)
+    assert np.allclose(c[:, 0], [0.5, 0.25]) and np.allclose(psnr[:, 0], [20.0, 40.0])
+
+
+def test_ssim_restatement_matches_oracle_and_basic_properties():
+    from oracle import pds_oracle as O
+    from pnp_pds_b200.utils.utils_eval import eval_psnr, eval_ssim
+    rng = np.random.default_rng(0)
+    a = rng.random((3, 40, 32))
+    b = np.clip(a + 0.05 * rng.standard_normal(a.shape), 0, 1)
+    assert abs(eval_ssim(a, b) - O.eval_ssim(a, b)) < 1e-12
+    assert abs(eval_ssim(a, a) - 1.0) < 1e-12
+    g = rng.random((40, 32))
+    assert 0 < eval_ssim(g, np.clip(g + 0.05 * rng.standard_normal(g.shape), 0, 1)) < 1
+    assert abs(eval_psnr(a, b) - O.eval_psnr(a, b)) < 1e-12
+
+
+def test_shard_range_partitions():
+    from pnp_pds_b200.parallel import shard_range
+    for n in (0, 1, 7, 256, 2560):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+from pnp_pds_b200.parallel import init_distributed, shard_range, gather_rows
+rank, local_rank, world = init_distributed("gloo")
+n_items = 7
+lo, hi = shard_range(n_items, rank, world)
+rows = np.stack([[i, 10.0 * i + 0.5, -i] for i in range(lo, hi)]) if hi > lo else np.zeros((0, 3))
+out = gather_rows(rows, n_items)
+exp = np.stack([[i, 10.0 * i + 0.5, -i] for i in range(n_items)])
+assert out.shape == (n_items, 3) and np.array_equal(out, exp), out
+print("rank", rank, "ok")
+"""
+
+
+def test_gather_rows_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
