@@ -74,7 +74,7 @@ def test_test_iter_signature_and_errors(g_loops, assets):
     assert x.dtype == np.float32 and x.shape == (64, 64) and np.all(s05 == 0.5)
     assert c.shape == psnr.shape == ssim.shape == (10,) and avg > 0
     assert rel_l2(x, g_loops[f"{tag}/x_10"]) < REL_L2_GATE
-    assert np.isfinite(ssim[-1]) and abs(ssim[-1] - O.eval_ssim(g_loops[f"{tag}/x_true"], x)) < 1e-9
+    assert np.isfinite(ssim[-1]) and abs(ssim[-1] - O.eval_ssim(g_loops[f"{tag}/x_true"], x)) < 1e-6
     with pytest.raises(ValueError):
         iteration.test_iter(*args, "no-such-method", 1, 1.0)
     with pytest.raises(ValueError):

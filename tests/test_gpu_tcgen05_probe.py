@@ -41,7 +41,7 @@ def _expected(a_off, sbo):
 
 
 CASES = [(0, 1024), (0, 2048), (128, 2048), (256, 2048), (2048 + 128, 2048), (2 * 2048 + 256, 2048), (32, 2048), (128 + 64, 2048),
-         (3 * 128, 2048), (7 * 128, 2048)]
+         (3 * 128, 2048), (7 * 128, 2048), (0, 1280), (128, 1280), (1280 + 256, 1280), (2 * 1280 + 128 + 96, 1280), (0, 1152), (384, 1152)]
 
 
 def test_umma_descriptor_addressing():
@@ -60,7 +60,9 @@ def test_umma_descriptor_addressing():
     with open(os.path.join(OUT, "probe_umma.json"), "w") as f:
         json.dump(report, f, indent=1)
     print("UMMA addressing models:", ok_models)
-    assert ok_models["base0"] or ok_models["baseoff"], report["summary"]
+    # measured on B200: the swizzle phase comes from the address bits (base_offset must stay 0), for any
+    # 128-byte-aligned start and any stride-byte-offset that is a multiple of 128
+    assert ok_models["base0"], report["summary"]
 
 
 def test_tma_box_swizzle_and_oob():
