@@ -154,7 +154,7 @@ int pds_debug_set_tc_variant(pds_handle_t h, int variant);
 /* one tcgen05.mma (M=128, N=16, K=16, B = identity) over a shared-memory region whose 16-byte chunk c
  * holds (c & 1023, c >> 10) repeated; out_host[128][16] therefore reveals which chunk fed every (row, k) */
 int pds_debug_umma_probe(unsigned a_off, unsigned sbo, unsigned base_off, unsigned region_bytes, float* out_host);
-/* one activation-tile TMA box load at (x, y, plane_index); out_host receives the 36864 shared-memory bytes */
+/* one activation-tile TMA box load at (x, y, plane_index); out_host receives the 23040 shared-memory bytes (18 rows x 10 pixels x 128 B) */
 int pds_debug_tma_probe(const void* act_dev, int nimg, int H, int W, int x, int y, int plane_index, void* out_host);
 
 #ifdef __cplusplus

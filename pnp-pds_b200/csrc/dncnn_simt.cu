@@ -10,6 +10,8 @@
 //
 // Inter-layer activations are [img][2][H][W][64] fp16: plane 0 holds hi = fp16(v), plane 1 holds
 // lo = fp16(v - hi), so hi + lo carries ~22 mantissa bits and both engines read the same data.
+#include <cstring>
+
 #include "kernels.cuh"
 
 namespace pds {
@@ -40,28 +42,27 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo)
 }
 
 // ------------------------------------------------------------------ first layer
-constexpr int kFirstThreads = 256;
+// One thread = one pixel x all 64 output channels.  The layer's weights travel as a __grid_constant__
+// kernel parameter, so every FFMA takes its weight straight from the constant bank (no load
+// instructions in the 9*Cin*64-FMA body); the 9*Cin inputs are read once per thread through L1.
+constexpr int kFirstThreads = 128;
+
+template <int CIN>
+struct FirstW {
+  float w[9 * CIN][64];   // k = tap*CIN + ci
+  float b[64];
+};
 
 template <int CIN>
 __global__ void __launch_bounds__(kFirstThreads) conv_first_kernel(int nimg, int H, int W, const float* __restrict__ in,
-                                                                   const float* __restrict__ wk, const float* __restrict__ bias,
-                                                                   float slope, int clamp_in, __half* __restrict__ act) {
-  __shared__ __align__(16) float ws[9 * CIN * 64];
-  __shared__ float bs[64];
-  for (int i = threadIdx.x; i < 9 * CIN * 64; i += kFirstThreads) ws[i] = wk[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+                                                                   const __grid_constant__ FirstW<CIN> wk, float slope, int clamp_in,
+                                                                   __half* __restrict__ act) {
   const int hw = H * W;
   const long long P = (long long)nimg * hw;
-  const int og = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  for (long long pg = blockIdx.x; pg * 32 < P; pg += gridDim.x) {
-    const long long pix = pg * 32 + pl;
-    if (pix >= P) continue;
+  for (long long pix = (long long)blockIdx.x * kFirstThreads + threadIdx.x; pix < P; pix += (long long)gridDim.x * kFirstThreads) {
     const int img = (int)(pix / hw), rem = (int)(pix - (long long)img * hw);
     const int y = rem / W, x = rem - y * W;
-    float acc[8];
-#pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = bs[og * 8 + o];
+    float v[9 * CIN];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
       const int yy = y + dy - 1;
@@ -71,29 +72,47 @@ __global__ void __launch_bounds__(kFirstThreads) conv_first_kernel(int nimg, int
         const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
-          float v = 0.f;
+          float t = 0.f;
           if (ok) {
-            v = __ldg(in + ((size_t)(img * CIN + ci) * H + yy) * W + xx);
-            if (clamp_in) v = fminf(fmaxf(v, 0.f), 1.f);
+            t = __ldg(in + ((size_t)(img * CIN + ci) * H + yy) * W + xx);
+            if (clamp_in) t = fminf(fmaxf(t, 0.f), 1.f);
           }
-          const float4* wp = reinterpret_cast<const float4*>(&ws[((dy * 3 + dx) * CIN + ci) * 64 + og * 8]);
-          const float4 w0 = wp[0], w1 = wp[1];
-          acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
-          acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
-          acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
-          acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+          v[(dy * 3 + dx) * CIN + ci] = t;
         }
       }
     }
+    __half* o_hi = act + (((size_t)img * 2 + 0) * hw + rem) * 64;
+    __half* o_lo = act + (((size_t)img * 2 + 1) * hw + rem) * 64;
 #pragma unroll
-    for (int o = 0; o < 8; ++o) acc[o] = leaky(acc[o], slope);
-    uint4 hi, lo;
-    pack8(acc, hi, lo);
-    const size_t o_hi = (((size_t)img * 2 + 0) * hw + rem) * 64 + og * 8;
-    const size_t o_lo = (((size_t)img * 2 + 1) * hw + rem) * 64 + og * 8;
-    *reinterpret_cast<uint4*>(act + o_hi) = hi;
-    *reinterpret_cast<uint4*>(act + o_lo) = lo;
+    for (int g = 0; g < 8; ++g) {
+      float acc[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = wk.b[g * 8 + o];
+#pragma unroll
+      for (int k = 0; k < 9 * CIN; ++k)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[o] = fmaf(v[k], wk.w[k][g * 8 + o], acc[o]);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) acc[o] = leaky(acc[o], slope);
+      uint4 hi, lo;
+      pack8(acc, hi, lo);
+      *reinterpret_cast<uint4*>(o_hi + g * 8) = hi;
+      *reinterpret_cast<uint4*>(o_lo + g * 8) = lo;
+    }
   }
+}
+
+template <int CIN>
+cudaError_t launch_first_t(int nimg, int H, int W, const float* in, const DncnnLayerW& L, float slope, int clamp_in, __half* act_out,
+                           cudaStream_t st) {
+  FirstW<CIN> wk;
+  std::memcpy(wk.w, L.w_first_host, sizeof(wk.w));
+  std::memcpy(wk.b, L.bias_host, sizeof(wk.b));
+  const long long P = (long long)nimg * H * W;
+  long long blocks = (P + kFirstThreads - 1) / kFirstThreads;
+  const int grid = (int)(blocks < 148 * 32 ? (blocks < 1 ? 1 : blocks) : 148 * 32);
+  conv_first_kernel<CIN><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, wk, slope, clamp_in, act_out);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ middle layers (fp32 SIMT)
@@ -295,14 +314,9 @@ cudaError_t launch_last_t(int nimg, int H, int W, const __half* act_in, const Dn
 
 cudaError_t launch_conv_first(int nimg, int C, int H, int W, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
                               __half* act_out, cudaStream_t st) {
-  const long long P = (long long)nimg * H * W;
-  long long groups = (P + 31) / 32;
-  int grid = (int)(groups < 148 * 8 ? groups : 148 * 8);
-  if (grid < 1) grid = 1;
-  if (C == 1) conv_first_kernel<1><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, L.w_first, L.bias, slope, clamp_in, act_out);
-  else if (C == 3) conv_first_kernel<3><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, L.w_first, L.bias, slope, clamp_in, act_out);
-  else return cudaErrorInvalidValue;
-  return cudaGetLastError();
+  if (C == 1) return launch_first_t<1>(nimg, H, W, in, L, slope, clamp_in, act_out, st);
+  if (C == 3) return launch_first_t<3>(nimg, H, W, in, L, slope, clamp_in, act_out, st);
+  return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_conv_mid_simt(int nimg, int H, int W, const __half* act_in, const DncnnLayerW& L, float slope, __half* act_out,

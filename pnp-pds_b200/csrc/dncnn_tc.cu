@@ -10,17 +10,21 @@
 //     a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into ONE fp32 TMEM accumulator (108 tcgen05.mma per tile),
 //     which recovers ~2^-22 relative operand precision — needed for the 1e-4 iterate gate
 //     (single-pass fp16 misses it).
-//   * the activation halo tile (18 rows x 16 pixels x 64 ch, one per hi/lo plane) is fetched by
+//   * the activation halo tile (18 rows x 10 pixels x 64 ch, one per hi/lo plane) is fetched by
 //     ONE 4-D TMA box each with SWIZZLE_128B; out-of-image pixels are zero-filled by TMA, which is
 //     exactly the convolution's zero padding.  All 9 taps read that single tile: the A descriptor
-//     of tap (dy,dx) starts at pixel-row offset (dy*16+dx)*128 B with SBO = one tile row (2048 B).
+//     of tap (dy,dx) starts at pixel-row offset (dy*10+dx)*128 B with SBO = one tile row (1280 B).
+//     (Probed on B200, tests/test_gpu_tcgen05_probe.py: the 128B-swizzle phase is taken from the
+//     shared-memory ADDRESS bits, so any 128-B-aligned start and any SBO multiple of 128 B work with
+//     base_offset = 0.)
 //   * the layer's weights (2 x 9 x 64x64 fp16, pre-swizzled on the host) stay resident in shared
 //     memory for the whole persistent CTA (147 KB), loaded once with cp.async.bulk.
-//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-//     warps 2-5 = epilogue (tcgen05.ld -> bias + LeakyReLU -> hi/lo split -> 16-byte stores).
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane,
+//     warp-uniform control flow so descriptors live in uniform registers), warps 2-5 = epilogue
+//     (tcgen05.ld -> bias + LeakyReLU -> hi/lo split -> 16-byte stores).
 //     The accumulator is double-buffered in TMEM (2 x 64 columns) so the epilogue of tile i
-//     overlaps the MMAs of tile i+1; the hi and lo planes have separate full/empty barriers so
-//     the next tile's hi plane streams in while the lo-plane MMAs of the current tile run.
+//     overlaps the MMAs of tile i+1; activation planes go through a 3-slot ring (hi_t, lo_t,
+//     hi_t+1, ...) so the producer runs up to three planes ahead of the tensor pipe.
 #include <cuda.h>
 
 #include "kernels.cuh"
@@ -30,11 +34,13 @@ namespace pds {
 namespace {
 
 constexpr int kTileRows = 16, kTileCols = 8;          // output tile (M = 128)
-constexpr int kHaloRows = 18, kHaloPitch = 16;        // pixels
-constexpr uint32_t kPlaneBytes = kHaloRows * kHaloPitch * 128;   // 36864
+constexpr int kHaloRows = 18, kHaloPitch = 10;        // pixels
+constexpr uint32_t kPlaneBytes = kHaloRows * kHaloPitch * 128;   // 23040 bytes landed by one TMA box
+constexpr uint32_t kPlaneSlot = 23 * 1024;                        // slot stride: keeps every slot 1024-B aligned
+constexpr int kSlots = 3;
 constexpr uint32_t kWTile = 64 * 128;                             // 8192: one (split, tap) 64x64 fp16 tile
 constexpr uint32_t kWBytes = 2 * 9 * kWTile;                      // 147456
-constexpr uint32_t kOffW = 0, kOffA0 = kWBytes, kOffA1 = kOffA0 + kPlaneBytes, kOffBar = kOffA1 + kPlaneBytes;
+constexpr uint32_t kOffW = 0, kOffA = kWBytes, kOffBar = kOffA + kSlots * kPlaneSlot;
 constexpr uint32_t kOffBias = kOffBar + 128, kSmemUsed = kOffBias + 256;
 constexpr uint32_t kSmemBytes = kSmemUsed + 1024;                 // slack for manual 1024-B alignment
 constexpr int kThreads = 192;
@@ -128,16 +134,53 @@ __device__ __forceinline__ void store_half_row(__half* dst_hi, __half* dst_lo, c
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int c = q * 8 + 2 * k;
-      const float v0 = leaky(__uint_as_float(r[c]) + bias_s[c0 + c], slope);
-      const float v1 = leaky(__uint_as_float(r[c + 1]) + bias_s[c0 + c + 1], slope);
-      __half h0, l0, h1, l1;
-      split_hi_lo(v0, h0, l0);
-      split_hi_lo(v1, h1, l1);
-      h[k] = __halves2half2(h0, h1);
-      l[k] = __halves2half2(l0, l1);
+      const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
+      float v0 = __uint_as_float(r[c]) + b.x, v1 = __uint_as_float(r[c + 1]) + b.y;
+      v0 = fmaxf(v0, v0 * slope);            // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
+      v1 = fmaxf(v1, v1 * slope);
+      const __half2 hh = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hh);
+      h[k] = hh;
+      l[k] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
     }
     *reinterpret_cast<uint4*>(dst_hi + c0 + q * 8) = hi;
     *reinterpret_cast<uint4*>(dst_lo + c0 + q * 8) = lo;
+  }
+}
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// All MMAs of one activation plane (36 k-steps; hi plane: x w_hi and x w_lo, lo plane: x w_hi).
+// a_lo / w_lo are the low descriptor words of the plane / weight bases; every offset is an immediate.
+template <bool HI_PLANE>
+__device__ __forceinline__ void issue_plane(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo, bool fresh) {
+  constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
+  constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
+      const uint32_t bo = (uint32_t)(tap * (int)kWTile + k * 32) >> 4;
+      const uint64_t ad = desc64(a_lo + ao, kHiA);
+      if (HI_PLANE) {
+        umma_f16(d_tmem, ad, desc64(w_lo + bo, kHiB), kIdesc, (tap == 0 && k == 0 && fresh) ? 0u : 1u);
+        umma_f16(d_tmem, ad, desc64(w_lo + bo + ((9u * kWTile) >> 4), kHiB), kIdesc, 1u);
+      } else {
+        umma_f16(d_tmem, ad, desc64(w_lo + bo, kHiB), kIdesc, 1u);
+      }
+    }
   }
 }
 
@@ -146,19 +189,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t sW = base + kOffW, sA[2] = {base + kOffA0, base + kOffA1}, sBar = base + kOffBar;
-  const uint32_t bFull[2] = {sBar + 0, sBar + 8}, bEmpty[2] = {sBar + 16, sBar + 24}, bW = sBar + 32;
-  const uint32_t bTFull[2] = {sBar + 40, sBar + 48}, bTEmpty[2] = {sBar + 56, sBar + 64};
-  const uint32_t sTmemSlot = sBar + 80;
+  const uint32_t sW = base + kOffW, sA = base + kOffA, sBar = base + kOffBar;
+  // barriers: full[3] @0, empty[3] @24, wfull @48, tfull[2] @56, tempty[2] @72, tmem slot @96
+  const uint32_t bFull = sBar, bEmpty = sBar + 24, bW = sBar + 48, bTFull = sBar + 56, bTEmpty = sBar + 72;
+  const uint32_t sTmemSlot = sBar + 96;
   float* bias_s = reinterpret_cast<float*>(gbase + kOffBias);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    mbar_init(bFull[0], 1); mbar_init(bFull[1], 1);
-    mbar_init(bEmpty[0], 1); mbar_init(bEmpty[1], 1);
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(bFull + 8 * i, 1);
+      mbar_init(bEmpty + 8 * i, 1);
+    }
     mbar_init(bW, 1);
-    mbar_init(bTFull[0], 1); mbar_init(bTFull[1], 1);
-    mbar_init(bTEmpty[0], 4); mbar_init(bTEmpty[1], 4);
+    mbar_init(bTFull, 1); mbar_init(bTFull + 8, 1);
+    mbar_init(bTEmpty, 4); mbar_init(bTEmpty + 8, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -170,65 +215,56 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar + 80);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar + 96);
 
   const int per_img = a.tiles_x * a.tiles_y;
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
+    if (elect_one()) {
       mbar_expect_tx(bW, kWBytes);
       for (int i = 0; i < 18; ++i) bulk_load(sW + i * kWTile, reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)i * kWTile, kWTile, bW);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-        const int img = tile / per_img, rem = tile - img * per_img;
-        const int y0 = (rem / a.tiles_x) * kTileRows, x0 = (rem % a.tiles_x) * kTileCols;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          mbar_wait(bEmpty[p], (uint32_t)((it & 1) ^ 1));
-          mbar_expect_tx(bFull[p], kPlaneBytes);
-          tma_load_4d(sA[p], &tmap, bFull[p], 0, x0 - 1, y0 - 1, img * 2 + p);
-        }
-      }
     }
     __syncwarp();
+    uint32_t j = 0;     // plane sequence number: 2*it + p
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y0 = (rem / a.tiles_x) * kTileRows, x0 = (rem % a.tiles_x) * kTileCols;
+#pragma unroll
+      for (int p = 0; p < 2; ++p, ++j) {
+        const uint32_t slot = j % kSlots, use = j / kSlots;
+        mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bFull + 8 * slot, kPlaneBytes);
+          tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
+        }
+        __syncwarp();
+      }
+    }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      mbar_wait(bW, 0);
-      int it = 0;
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(bTEmpty[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 64u;
-        uint32_t accumulate = 0;
-#pragma unroll 1
-        for (int p = 0; p < 2; ++p) {
-          mbar_wait(bFull[p], (uint32_t)(it & 1));
-          tc_fence_after();
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_row = sA[p] + (uint32_t)(dy * kHaloPitch + dx) * 128u;
-            const uint32_t boff = (a.variant & 1) ? ((a_row >> 7) & 7u) : 0u;
+    // ------------------------------------------------------------ MMA issuer
+    mbar_wait(bW, 0);
+    const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
+    uint32_t j = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+      const uint32_t d_tmem = tmem_base + acc * 64u;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint64_t ad = make_desc(a_row + k * 32, kHaloPitch * 128, boff);
-              const uint64_t bd_hi = make_desc(sW + (uint32_t)tap * kWTile + k * 32, 1024, 0);
-              umma_f16(d_tmem, ad, bd_hi, kIdesc, accumulate);
-              accumulate = 1;
-              if (p == 0) {
-                const uint64_t bd_lo = make_desc(sW + (uint32_t)(9 + tap) * kWTile + k * 32, 1024, 0);
-                umma_f16(d_tmem, ad, bd_lo, kIdesc, 1);
-              }
-            }
-          }
-          umma_commit(bEmpty[p]);     // plane p may be overwritten once these MMAs retire
+      for (int p = 0; p < 2; ++p, ++j) {
+        const uint32_t slot = j % kSlots, use = j / kSlots;
+        mbar_wait(bFull + 8 * slot, use & 1);
+        tc_fence_after();
+        const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+        if (elect_one()) {
+          if (p == 0) issue_plane<true>(d_tmem, a_lo, w_lo, true);
+          else issue_plane<false>(d_tmem, a_lo, w_lo, false);
+          umma_commit(bEmpty + 8 * slot);              // slot may be overwritten once these MMAs retire
+          if (p == 1) umma_commit(bTFull + 8 * acc);   // accumulator complete
         }
-        umma_commit(bTFull[acc]);     // accumulator complete
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     const int q = warp & 3;
@@ -239,17 +275,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const int img = tile / per_img, rem = tile - img * per_img;
       const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
-      const int acc = it & 1;
-      mbar_wait(bTFull[acc], (uint32_t)((it >> 1) & 1));
+      const uint32_t acc = it & 1;
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 64u;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u;
       uint32_t r0[32], r1[32];
       tmem_ld32(taddr, r0);
       tmem_ld32(taddr + 32, r1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bTEmpty[acc]);
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
       if (y < a.H && x < a.W) {
         const size_t pix = (size_t)y * a.W + x;
         __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
@@ -340,7 +376,7 @@ __global__ void __launch_bounds__(128, 1) tma_probe_kernel(const __grid_constant
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* g = smem_raw + (base - raw);
-  const uint32_t sBar = base + kPlaneBytes;
+  const uint32_t sBar = base + kPlaneSlot;
   if (threadIdx.x == 0) {
     mbar_init(sBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -470,7 +506,7 @@ extern "C" int pds_debug_tma_probe(const void* act_dev, int nimg, int H, int W, 
   if (rc) return rc;
   uint4* d = nullptr;
   PDS_CUDA_OK(cudaMalloc(&d, kPlaneBytes));
-  const size_t smem = (size_t)kPlaneBytes + 64 + 1024;
+  const size_t smem = (size_t)kPlaneSlot + 64 + 1024;
   PDS_CUDA_OK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   tma_probe_kernel<<<1, 128, smem>>>(map, x, y, plane_index, d);
   PDS_CUDA_OK(cudaGetLastError());
