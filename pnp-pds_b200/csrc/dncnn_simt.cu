@@ -41,63 +41,92 @@ __device__ __forceinline__ void pack8(const float (&v)[8], uint4& hi, uint4& lo)
   }
 }
 
+__device__ __forceinline__ void st_global_256(void* p, const uint4 (&v)[2]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0].x), "r"(v[0].y), "r"(v[0].z), "r"(v[0].w),
+               "r"(v[1].x), "r"(v[1].y), "r"(v[1].z), "r"(v[1].w)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ first layer
-// One thread = one pixel x all 64 output channels.  The layer's weights travel as a __grid_constant__
-// kernel parameter, so every FFMA takes its weight straight from the constant bank (no load
-// instructions in the 9*Cin*64-FMA body); the 9*Cin inputs are read once per thread through L1.
+// One thread = 4 horizontally adjacent pixels x 16 output channels (64 fp32 accumulators); the 4 lanes
+// that share a pixel quad hold the 4 channel groups, so their 256-bit stores fill one full 128-byte
+// line per pixel and plane.  Weights sit in shared memory ([tap*Cin+ci][64], 16 B broadcast reads:
+// 4 LDS.128 feed 64 FMAs); the 3x6 input window per channel is read once per thread through L1.
 constexpr int kFirstThreads = 128;
 
 template <int CIN>
-struct FirstW {
-  float w[9 * CIN][64];   // k = tap*CIN + ci
-  float b[64];
-};
-
-template <int CIN>
-__global__ void __launch_bounds__(kFirstThreads) conv_first_kernel(int nimg, int H, int W, const float* __restrict__ in,
-                                                                   const __grid_constant__ FirstW<CIN> wk, float slope, int clamp_in,
-                                                                   __half* __restrict__ act) {
-  const int hw = H * W;
-  const long long P = (long long)nimg * hw;
-  for (long long pix = (long long)blockIdx.x * kFirstThreads + threadIdx.x; pix < P; pix += (long long)gridDim.x * kFirstThreads) {
-    const int img = (int)(pix / hw), rem = (int)(pix - (long long)img * hw);
-    const int y = rem / W, x = rem - y * W;
-    float v[9 * CIN];
+__global__ void __launch_bounds__(kFirstThreads, 4) conv_first_kernel(int nimg, int H, int W, const float* __restrict__ in,
+                                                                   const float* __restrict__ wk, const float* __restrict__ bias,
+                                                                   float slope, int clamp_in, __half* __restrict__ act) {
+  __shared__ __align__(16) float ws[9 * CIN * 64];
+  __shared__ __align__(16) float bs[64];
+  for (int i = threadIdx.x; i < 9 * CIN * 64; i += kFirstThreads) ws[i] = wk[i];
+  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int ocg = threadIdx.x & 3, ql = threadIdx.x >> 2;
+  const int qpr = (W + 3) >> 2;                        // pixel quads per row
+  const long long nquads = (long long)nimg * H * qpr;
+  const size_t hw = (size_t)H * W;
+  for (long long q = (long long)blockIdx.x * (kFirstThreads / 4) + ql; q < nquads; q += (long long)gridDim.x * (kFirstThreads / 4)) {
+    const int img = (int)(q / ((long long)H * qpr));
+    const int r = (int)(q - (long long)img * H * qpr);
+    const int y = r / qpr, x0 = (r - y * qpr) * 4;
+    float acc[4][16];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int yy = y + dy - 1;
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) {
-        const int xx = x + dx - 1;
-        const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
+      for (int o = 0; o < 16; ++o) acc[p][o] = bs[ocg * 16 + o];
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
+    for (int ci = 0; ci < CIN; ++ci) {
+      float v[3][6];            // 3x6 input window of this channel (only one channel live at a time)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y + dy - 1;
+        const float* row = in + ((size_t)(img * CIN + ci) * H + yy) * W;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+          const int xx = x0 + j - 1;
           float t = 0.f;
-          if (ok) {
-            t = __ldg(in + ((size_t)(img * CIN + ci) * H + yy) * W + xx);
+          if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            t = __ldg(row + xx);
             if (clamp_in) t = fminf(fmaxf(t, 0.f), 1.f);
           }
-          v[(dy * 3 + dx) * CIN + ci] = t;
+          v[dy][j] = t;
         }
       }
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4* wp = reinterpret_cast<const float4*>(&ws[((dy * 3 + dx) * CIN + ci) * 64 + ocg * 16]);
+          float w[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = wp[j];
+            w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
+          }
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float a = v[dy][p + dx];
+#pragma unroll
+            for (int o = 0; o < 16; ++o) acc[p][o] = fmaf(a, w[o], acc[p][o]);
+          }
+        }
     }
-    __half* o_hi = act + (((size_t)img * 2 + 0) * hw + rem) * 64;
-    __half* o_lo = act + (((size_t)img * 2 + 1) * hw + rem) * 64;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      float acc[8];
+    for (int p = 0; p < 4; ++p) {
+      if (x0 + p >= W) continue;
+      const size_t pix = (size_t)y * W + x0 + p;
+      uint4 hi[2], lo[2];
 #pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = wk.b[g * 8 + o];
+      for (int g = 0; g < 2; ++g) {
+        float t8[8];
 #pragma unroll
-      for (int k = 0; k < 9 * CIN; ++k)
-#pragma unroll
-        for (int o = 0; o < 8; ++o) acc[o] = fmaf(v[k], wk.w[k][g * 8 + o], acc[o]);
-#pragma unroll
-      for (int o = 0; o < 8; ++o) acc[o] = leaky(acc[o], slope);
-      uint4 hi, lo;
-      pack8(acc, hi, lo);
-      *reinterpret_cast<uint4*>(o_hi + g * 8) = hi;
-      *reinterpret_cast<uint4*>(o_lo + g * 8) = lo;
+        for (int o = 0; o < 8; ++o) t8[o] = leaky(acc[p][g * 8 + o], slope);
+        pack8(t8, hi[g], lo[g]);
+      }
+      st_global_256(act + (((size_t)img * 2 + 0) * hw + pix) * 64 + ocg * 16, hi);
+      st_global_256(act + (((size_t)img * 2 + 1) * hw + pix) * 64 + ocg * 16, lo);
     }
   }
 }
@@ -105,13 +134,10 @@ __global__ void __launch_bounds__(kFirstThreads) conv_first_kernel(int nimg, int
 template <int CIN>
 cudaError_t launch_first_t(int nimg, int H, int W, const float* in, const DncnnLayerW& L, float slope, int clamp_in, __half* act_out,
                            cudaStream_t st) {
-  FirstW<CIN> wk;
-  std::memcpy(wk.w, L.w_first_host, sizeof(wk.w));
-  std::memcpy(wk.b, L.bias_host, sizeof(wk.b));
-  const long long P = (long long)nimg * H * W;
-  long long blocks = (P + kFirstThreads - 1) / kFirstThreads;
+  const long long nquads = (long long)nimg * H * ((W + 3) / 4);
+  long long blocks = (nquads + kFirstThreads / 4 - 1) / (kFirstThreads / 4);
   const int grid = (int)(blocks < 148 * 32 ? (blocks < 1 ? 1 : blocks) : 148 * 32);
-  conv_first_kernel<CIN><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, wk, slope, clamp_in, act_out);
+  conv_first_kernel<CIN><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, L.w_first, L.bias, slope, clamp_in, act_out);
   return cudaGetLastError();
 }
 

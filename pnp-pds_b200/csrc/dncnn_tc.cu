@@ -37,23 +37,38 @@ constexpr int kTileRows = 16, kTileCols = 8;          // output tile (M = 128)
 constexpr int kHaloRows = 18, kHaloPitch = 10;        // pixels
 constexpr uint32_t kPlaneBytes = kHaloRows * kHaloPitch * 128;   // 23040 bytes landed by one TMA box
 constexpr uint32_t kPlaneSlot = 23 * 1024;                        // slot stride: keeps every slot 1024-B aligned
-constexpr int kSlots = 3;
-constexpr uint32_t kWTile = 64 * 128;                             // 8192: one (split, tap) 64x64 fp16 tile
-constexpr uint32_t kWBytes = 2 * 9 * kWTile;                      // 147456
-constexpr uint32_t kOffW = 0, kOffA = kWBytes, kOffBar = kOffA + kSlots * kPlaneSlot;
-constexpr uint32_t kOffBias = kOffBar + 128, kSmemUsed = kOffBias + 256;
-constexpr uint32_t kSmemBytes = kSmemUsed + 1024;                 // slack for manual 1024-B alignment
 constexpr int kThreads = 192;
-constexpr uint32_t kTmemCols = 128;
-constexpr uint32_t kIdesc = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescBase = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((128u >> 4) << 24) /*M=128*/;
+
+// Compile-time geometry for a layer with NW output channels (rows of the B operand per hi/lo split):
+//   NW = 64 : the 64->64 body layers;   NW = 16 : the last layer (Cout = 1|3, zero-padded to 16 rows).
+template <int NW>
+struct Geo {
+  static constexpr uint32_t kWTile = NW * 128;                 // one (tap, split) NW x 64 fp16 tile
+  static constexpr uint32_t kWBytes = 9 * 2 * kWTile;          // 147456 (NW=64) / 36864 (NW=16), 1024-multiples
+  static constexpr int kSlots = NW == 64 ? 3 : 6;              // activation-plane ring depth
+  static constexpr uint32_t kOffA = kWBytes, kOffBar = kOffA + kSlots * kPlaneSlot;
+  static constexpr uint32_t kOffBias = kOffBar + 192, kSmemUsed = kOffBias + 256;
+  static constexpr uint32_t kSmemBytes = kSmemUsed + 1024;     // slack for manual 1024-B alignment
+  static constexpr uint32_t kAccCols = 2 * NW;                 // cols [0,NW): a*w_hi ; [NW,2NW): a_hi*w_lo (summed in the epilogue)
+  static constexpr uint32_t kTmemCols = 4 * NW < 32 ? 32 : 4 * NW;   // 2 accumulator stages
+  static constexpr uint32_t kIdescLo = kIdescBase | ((uint32_t)(NW >> 3) << 17);
+  static constexpr uint32_t kIdescHi = kIdescBase | ((uint32_t)((2 * NW) >> 3) << 17);
+};
 
 struct TcArgs {
   const __half* w_img;
   const float* bias;
-  __half* out;
+  __half* out;            // body layers: next activation buffer
   float slope;
   int H, W, nimg, tiles_x, tiles_y, ntiles;
   int variant;
+  // last layer only
+  const float* net_in;    // (nimg, C, H, W) network input (residual)
+  float* out_f32;         // (nimg, C, H, W)
+  int C;
+  float res_sign;
+  int clamp;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,27 +139,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void store_half_row(__half* dst_hi, __half* dst_lo, const uint32_t (&r)[32], const float* bias_s, int c0,
-                                               float slope) {
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+// 32 channels [c0, c0+32) of one pixel: v = d0 + d1 + bias -> LeakyReLU -> (hi, lo) fp16, written as full
+// 32-byte sectors (one 256-bit store per 16 channels and plane).
+__device__ __forceinline__ void store_half_row(__half* dst_hi, __half* dst_lo, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
+                                               const float* bias_s, int c0, float slope) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint4 hi, lo;
-    __half2* h = reinterpret_cast<__half2*>(&hi);
-    __half2* l = reinterpret_cast<__half2*>(&lo);
+  for (int q = 0; q < 2; ++q) {
+    uint32_t hi[8], lo[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = q * 8 + 2 * k;
+    for (int k = 0; k < 8; ++k) {
+      const int c = q * 16 + 2 * k;
       const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
-      float v0 = __uint_as_float(r[c]) + b.x, v1 = __uint_as_float(r[c + 1]) + b.y;
+      float v0 = (__uint_as_float(d0[c]) + __uint_as_float(d1[c])) + b.x;
+      float v1 = (__uint_as_float(d0[c + 1]) + __uint_as_float(d1[c + 1])) + b.y;
       v0 = fmaxf(v0, v0 * slope);            // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
       v1 = fmaxf(v1, v1 * slope);
       const __half2 hh = __floats2half2_rn(v0, v1);
       const float2 hf = __half22float2(hh);
-      h[k] = hh;
-      l[k] = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
     }
-    *reinterpret_cast<uint4*>(dst_hi + c0 + q * 8) = hi;
-    *reinterpret_cast<uint4*>(dst_lo + c0 + q * 8) = lo;
+    st_global_256(dst_hi + c0 + q * 16, hi);
+    st_global_256(dst_lo + c0 + q * 16, lo);
   }
 }
 
@@ -160,10 +183,15 @@ __device__ __forceinline__ uint32_t elect_one() {
 
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-// All MMAs of one activation plane (36 k-steps; hi plane: x w_hi and x w_lo, lo plane: x w_hi).
+// All MMAs of one activation plane (36 k-steps).  The weight image keeps, per tap, w_hi (NW rows) directly
+// followed by w_lo (NW rows), so the hi plane multiplies against B = [w_hi ; w_lo] as ONE N=2*NW MMA
+// (columns [0,NW) accumulate a_hi*w_hi, columns [NW,2NW) a_hi*w_lo): the 4 KB A tile is read from shared
+// memory once for two products — the SS-mode MMA is bound by shared-memory operand reads (~100 B/clk
+// measured), so bytes per MAC is what matters.  The lo plane needs only a_lo*w_hi: N=NW into [0,NW).
 // a_lo / w_lo are the low descriptor words of the plane / weight bases; every offset is an immediate.
-template <bool HI_PLANE>
-__device__ __forceinline__ void issue_plane(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo, bool fresh) {
+template <int NW, bool HI_PLANE>
+__device__ __forceinline__ void issue_plane(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
+  using G = Geo<NW>;
   constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
   constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
 #pragma unroll
@@ -172,28 +200,26 @@ __device__ __forceinline__ void issue_plane(uint32_t d_tmem, uint32_t a_lo, uint
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
-      const uint32_t bo = (uint32_t)(tap * (int)kWTile + k * 32) >> 4;
-      const uint64_t ad = desc64(a_lo + ao, kHiA);
-      if (HI_PLANE) {
-        umma_f16(d_tmem, ad, desc64(w_lo + bo, kHiB), kIdesc, (tap == 0 && k == 0 && fresh) ? 0u : 1u);
-        umma_f16(d_tmem, ad, desc64(w_lo + bo + ((9u * kWTile) >> 4), kHiB), kIdesc, 1u);
-      } else {
-        umma_f16(d_tmem, ad, desc64(w_lo + bo, kHiB), kIdesc, 1u);
-      }
+      const uint32_t bo = (uint32_t)(tap * 2 * (int)G::kWTile + k * 32) >> 4;
+      if (HI_PLANE) umma_f16(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), G::kIdescHi, (tap == 0 && k == 0) ? 0u : 1u);
+      else umma_f16(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), G::kIdescLo, 1u);
     }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+template <int NW>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  using G = Geo<NW>;
+  constexpr int kSlots = G::kSlots;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
-  const uint32_t sW = base + kOffW, sA = base + kOffA, sBar = base + kOffBar;
-  // barriers: full[3] @0, empty[3] @24, wfull @48, tfull[2] @56, tempty[2] @72, tmem slot @96
-  const uint32_t bFull = sBar, bEmpty = sBar + 24, bW = sBar + 48, bTFull = sBar + 56, bTEmpty = sBar + 72;
-  const uint32_t sTmemSlot = sBar + 96;
-  float* bias_s = reinterpret_cast<float*>(gbase + kOffBias);
+  const uint32_t sW = base, sA = base + G::kOffA, sBar = base + G::kOffBar;
+  // barriers: full[6] @0, empty[6] @48, wfull @96, tfull[2] @104, tempty[2] @120, tmem slot @136
+  const uint32_t bFull = sBar, bEmpty = sBar + 48, bW = sBar + 96, bTFull = sBar + 104, bTEmpty = sBar + 120;
+  const uint32_t sTmemSlot = sBar + 136;
+  float* bias_s = reinterpret_cast<float*>(gbase + G::kOffBias);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -207,22 +233,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (threadIdx.x >= 64 && threadIdx.x < 128) {
+    const int c = threadIdx.x - 64;
+    bias_s[c] = (NW == 64 || c < a.C) ? a.bias[c] : 0.f;
+  }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(G::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar + 96);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + G::kOffBar + 136);
 
   const int per_img = a.tiles_x * a.tiles_y;
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (warp-uniform loop, one elected lane issues)
     if (elect_one()) {
-      mbar_expect_tx(bW, kWBytes);
-      for (int i = 0; i < 18; ++i) bulk_load(sW + i * kWTile, reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)i * kWTile, kWTile, bW);
+      mbar_expect_tx(bW, G::kWBytes);
+      for (int i = 0; i < 18; ++i)
+        bulk_load(sW + i * G::kWTile, reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)i * G::kWTile, G::kWTile, bW);
     }
     __syncwarp();
     uint32_t j = 0;     // plane sequence number: 2*it + p
@@ -235,7 +265,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
         mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(bFull + 8 * slot, kPlaneBytes);
-          tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
+          if (a.variant & 4) tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, -1, -1, p);   // perf experiment: L2-resident loads
+          else tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
         }
         __syncwarp();
       }
@@ -249,7 +280,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
-      const uint32_t d_tmem = tmem_base + acc * 64u;
+      const uint32_t d_tmem = tmem_base + acc * G::kAccCols;
 #pragma unroll
       for (int p = 0; p < 2; ++p, ++j) {
         const uint32_t slot = j % kSlots, use = j / kSlots;
@@ -257,8 +288,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
         tc_fence_after();
         const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
         if (elect_one()) {
-          if (p == 0) issue_plane<true>(d_tmem, a_lo, w_lo, true);
-          else issue_plane<false>(d_tmem, a_lo, w_lo, false);
+          if (!(a.variant & 8)) {                       // perf experiment: bit 3 skips the MMAs
+            if (p == 0) issue_plane<NW, true>(d_tmem, a_lo, w_lo);
+            else issue_plane<NW, false>(d_tmem, a_lo, w_lo);
+          }
           umma_commit(bEmpty + 8 * slot);              // slot may be overwritten once these MMAs retire
           if (p == 1) umma_commit(bTFull + 8 * acc);   // accumulator complete
         }
@@ -278,20 +311,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
       const uint32_t acc = it & 1;
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u;
-      uint32_t r0[32], r1[32];
-      tmem_ld32(taddr, r0);
-      tmem_ld32(taddr + 32, r1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
-      if (y < a.H && x < a.W) {
-        const size_t pix = (size_t)y * a.W + x;
-        __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-        __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
-        store_half_row(o_hi, o_lo, r0, bias_s, 0, a.slope);
-        store_half_row(o_hi, o_lo, r1, bias_s, 32, a.slope);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * G::kAccCols;
+      if constexpr (NW == 64) {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 64, r2);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + 96, r3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+        if (y < a.H && x < a.W && !(a.variant & 2)) {     // perf experiment: bit 1 skips the stores
+          const size_t pix = (size_t)y * a.W + x;
+          __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+          __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
+          store_half_row(o_hi, o_lo, r0, r2, bias_s, 0, a.slope);
+          store_half_row(o_hi, o_lo, r1, r3, bias_s, 32, a.slope);
+        }
+      } else {
+        // last layer: columns [0,16) = a*w_hi, [16,32) = a_hi*w_lo; only the first C are real channels.
+        // out = clamp(sign * (conv + bias) + clamp(net_in))   (basic_models.py:36, denoiser.py:40-42, network_dncnn.py:77)
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+        if (y < a.H && x < a.W) {
+          const size_t pix = (size_t)y * a.W + x;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (c < a.C) {
+              const size_t g = ((size_t)img * a.C + c) * hw + pix;
+              float xin = __ldg(a.net_in + g);
+              if (a.clamp) xin = fminf(fmaxf(xin, 0.f), 1.f);
+              const float n = (__uint_as_float(r[c]) + __uint_as_float(r[16 + c])) + bias_s[c];
+              float o = a.res_sign > 0.f ? n + xin : xin - n;
+              if (a.clamp) o = fminf(fmaxf(o, 0.f), 1.f);
+              a.out_f32[g] = o;
+            }
+          }
+        }
       }
     }
   }
@@ -299,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_mid_tc_kernel(const __grid_c
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::kTmemCols) : "memory");
   }
 }
 
@@ -446,9 +507,11 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   int rc = make_act_map(&p->map[0], act0, nimg, H, W);
   if (!rc) rc = make_act_map(&p->map[1], act1, nimg, H, W);
   if (!rc) {
-    cudaError_t e = cudaFuncSetAttribute(conv_mid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<64>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<16>::kSmemBytes);
     if (e != cudaSuccess) {
-      set_error(std::string("cudaFuncSetAttribute(conv_mid_tc_kernel): ") + cudaGetErrorString(e));
+      set_error(std::string("cudaFuncSetAttribute(conv_tc_kernel): ") + cudaGetErrorString(e));
       rc = 1;
     }
   }
@@ -462,12 +525,7 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st) {
-  TcArgs a{};
-  a.w_img = L.w_mid_tc;
-  a.bias = L.bias;
-  a.out = plan->act[in_buf ^ 1];
-  a.slope = slope;
+static void fill_common(TcArgs& a, TcPlan* plan, int nimg, int variant) {
   a.H = plan->H;
   a.W = plan->W;
   a.nimg = nimg;
@@ -475,8 +533,34 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   a.tiles_y = (plan->H + kTileRows - 1) / kTileRows;
   a.ntiles = a.tiles_x * a.tiles_y * nimg;
   a.variant = variant;
+}
+
+cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st) {
+  TcArgs a{};
+  a.w_img = L.w_mid_tc;
+  a.bias = L.bias;
+  a.out = plan->act[in_buf ^ 1];
+  a.slope = slope;
+  a.C = 64;
+  fill_common(a, plan, nimg, variant);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  conv_mid_tc_kernel<<<grid, kThreads, kSmemBytes, st>>>(plan->map[in_buf], a);
+  conv_tc_kernel<64><<<grid, kThreads, Geo<64>::kSmemBytes, st>>>(plan->map[in_buf], a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in, float residual_sign,
+                                int clamp, float* out, int variant, cudaStream_t st) {
+  TcArgs a{};
+  a.w_img = L.w_last_tc;
+  a.bias = L.bias;
+  a.net_in = net_in;
+  a.out_f32 = out;
+  a.C = C;
+  a.res_sign = residual_sign;
+  a.clamp = clamp;
+  fill_common(a, plan, nimg, variant & 4);
+  const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
+  conv_tc_kernel<16><<<grid, kThreads, Geo<16>::kSmemBytes, st>>>(plan->map[in_buf], a);
   return cudaGetLastError();
 }
 

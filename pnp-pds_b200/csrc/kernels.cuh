@@ -67,11 +67,11 @@ cudaError_t launch_l1ball(const Dims& d, const float* s_in, const float* t, cons
 // ---- dncnn_*.cu ---------------------------------------------------------------
 // Activations between layers: [img][2 (hi,lo)][H][W][64] fp16 ("NHWC hi/lo planes").
 struct DncnnLayerW {
-  const float* w_first_host;  // HOST [9*Cin][64] (k = tap*Cin + ci): passed to the first-layer kernel by value
-  const float* bias_host;     // HOST [64] bias of the first layer
+  const float* w_first;   // [9*Cin][64]     (k = tap*Cin + ci)          first layer
   const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
-  const __half* w_mid_tc; // smem image for the tcgen05 engine: [2 (hi,lo)][9][64 oc][64 ci] fp16, 128B-swizzled rows
-  const float* w_last;    // [Cout][9][64 ci]                            last layer
+  const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][2 (hi,lo)][64 oc][64 ci] fp16, 128B-swizzled rows
+  const float* w_last;    // [Cout][9][64 ci]                            last layer (SIMT engine)
+  const __half* w_last_tc; // [9 taps][2][16 rows][64 ci] fp16 swizzled, rows >= Cout zero   last layer (tcgen05 engine)
   const float* bias;      // [Cout of this layer]
 };
 cudaError_t launch_conv_first(int nimg, int C, int H, int W, const float* in /*(nimg,C,H,W)*/, const DncnnLayerW& L, float slope,
@@ -87,6 +87,8 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 void tc_plan_destroy(TcPlan* p);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
+cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
+                                float residual_sign, int clamp, float* out, int variant, cudaStream_t st);
 int tc_num_sms();
 
 }  // namespace pds

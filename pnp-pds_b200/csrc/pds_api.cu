@@ -1,6 +1,7 @@
 // C-ABI of libpnp_pds.so: handle management, weight/operator set-up, stand-alone operators and
 // the resident PnP-PDS loop.  See include/pnp_pds.h for the contract and the reference
 // interfaces each entry point replaces.
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -43,7 +44,6 @@ struct pds_handle_s {
   float slope = 0.f, res_sign = 1.f;
   int clamp = 1;
   std::vector<DncnnLayerW> layers;
-  std::vector<float> first_w_host, first_b_host;
   __half* act[2] = {nullptr, nullptr};
   int chunk = 1;
   TcPlan* tc = nullptr;
@@ -158,7 +158,11 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
       }
       src ^= 1;
     }
-    PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
+    if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last_tc(h->tc, src, nimg, d.C, h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, h->tc_variant, st));
+    } else {
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
+    }
   }
   return 0;
 }
@@ -287,6 +291,7 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   pds_handle_s* h = new (std::nothrow) pds_handle_s();
   PDS_REQUIRE(h, "out of host memory");
   h->cfg = *cfg;
+  if (const char* v = std::getenv("PDS_TC_VARIANT")) h->tc_variant = std::atoi(v);   // perf-experiment switches (dncnn_tc.cu)
   h->d = Dims{cfg->batch, cfg->channels, cfg->height, cfg->width, cfg->height * cfg->width,
               cfg->channels * cfg->height * cfg->width};
   const size_t n = total_elems(h);
@@ -417,10 +422,10 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       for (int o = 0; o < co; ++o)
         for (int c = 0; c < ci; ++c)
           for (int tp = 0; tp < 9; ++tp) buf[((size_t)tp * ci + c) * 64 + o] = w[((size_t)o * ci + c) * 9 + tp];
-      h->first_w_host = buf;
-      h->first_b_host.assign(b, b + co);
-      L.w_first_host = h->first_w_host.data();
-      L.bias_host = h->first_b_host.data();
+      float* dw = nullptr;
+      PDS_TRY(dev_alloc(h, &dw, buf.size()));
+      PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
+      L.w_first = dw;
     } else if (l == depth - 1) {
       buf.assign((size_t)co * 9 * 64, 0.f);
       for (int o = 0; o < co; ++o)
@@ -430,6 +435,23 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dw, buf.size()));
       PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
       L.w_last = dw;
+      // tcgen05 engine: [tap][split][16 rows][64 ci] fp16, rows >= Cout are zero, 128B-swizzled rows
+      std::vector<__half> img((size_t)9 * 2 * 16 * 64, __float2half_rn(0.f));
+      for (int tp = 0; tp < 9; ++tp)
+        for (int o = 0; o < co; ++o)
+          for (int c = 0; c < 64; ++c) {
+            const float v = w[((size_t)o * ci + c) * 9 + tp];
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            const int chunk = (c >> 3) ^ (o & 7);
+            const size_t pos = ((size_t)(tp * 2) * 16 + o) * 64 + chunk * 8 + (c & 7);
+            img[pos] = hi;
+            img[(size_t)16 * 64 + pos] = lo;
+          }
+      __half* dh = nullptr;
+      PDS_TRY(dev_alloc(h, &dh, img.size()));
+      PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      L.w_last_tc = dh;
     } else {
       // SIMT engine: [ci][tap][oc] fp32
       buf.assign((size_t)64 * 9 * 64, 0.f);
@@ -440,7 +462,8 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dw, buf.size()));
       PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
       L.w_mid = dw;
-      // tcgen05 engine: shared-memory image [split][tap][oc][ci] fp16, K-major rows of 128 B,
+      // tcgen05 engine: shared-memory image [tap][split][oc][ci] fp16 (w_hi rows directly followed by the
+      // w_lo rows of the same tap, so one N=128 descriptor covers both), K-major rows of 128 B,
       // 16-byte chunk j of row oc stored at chunk (j ^ (oc & 7))  (SWIZZLE_128B)
       std::vector<__half> img((size_t)2 * 9 * 64 * 64);
       for (int tp = 0; tp < 9; ++tp)
@@ -450,9 +473,9 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
             const __half hi = __float2half_rn(v);
             const __half lo = __float2half_rn(v - __half2float(hi));
             const int chunk = (c >> 3) ^ (o & 7);
-            const size_t pos = ((size_t)tp * 64 + o) * 64 + chunk * 8 + (c & 7);
+            const size_t pos = ((size_t)(tp * 2) * 64 + o) * 64 + chunk * 8 + (c & 7);
             img[pos] = hi;
-            img[(size_t)9 * 64 * 64 + pos] = lo;
+            img[(size_t)64 * 64 + pos] = lo;
           }
       __half* dh = nullptr;
       PDS_TRY(dev_alloc(h, &dh, img.size()));
