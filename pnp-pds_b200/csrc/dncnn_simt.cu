@@ -48,26 +48,32 @@ __device__ __forceinline__ void st_global_256(void* p, const uint4 (&v)[2]) {
 }
 
 // ------------------------------------------------------------------ first layer
-// One thread = 4 horizontally adjacent pixels x 16 output channels (64 fp32 accumulators); the 4 lanes
-// that share a pixel quad hold the 4 channel groups, so their 256-bit stores fill one full 128-byte
-// line per pixel and plane.  Weights sit in shared memory ([tap*Cin+ci][64], 16 B broadcast reads:
-// 4 LDS.128 feed 64 FMAs); the 3x6 input window per channel is read once per thread through L1.
+// One thread = 4 horizontally adjacent pixels x 16 output channels (64 fp32 accumulators).  The 4 warps
+// of a block work on the SAME 32 pixel quads and each owns one group of 16 output channels, so the
+// weights a warp needs are warp-uniform: they travel as a __grid_constant__ kernel parameter and reach
+// the FFMAs through the constant bank / uniform registers (no shared-memory weight traffic; the
+// earlier LDS-broadcast version was LSU-bound).  Each lane then writes one full 32-byte sector per
+// pixel and plane with a 256-bit store.
 constexpr int kFirstThreads = 128;
 
 template <int CIN>
+struct FirstW {
+  float w[9 * CIN][64];   // k = tap*CIN + ci
+  float b[64];
+};
+
+template <int CIN>
 __global__ void __launch_bounds__(kFirstThreads, 4) conv_first_kernel(int nimg, int H, int W, const float* __restrict__ in,
-                                                                   const float* __restrict__ wk, const float* __restrict__ bias,
-                                                                   float slope, int clamp_in, __half* __restrict__ act) {
-  __shared__ __align__(16) float ws[9 * CIN * 64];
-  __shared__ __align__(16) float bs[64];
-  for (int i = threadIdx.x; i < 9 * CIN * 64; i += kFirstThreads) ws[i] = wk[i];
-  if (threadIdx.x < 64) bs[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  const int ocg = threadIdx.x & 3, ql = threadIdx.x >> 2;
+                                                                      const __grid_constant__ FirstW<CIN> wk, float slope, int clamp_in,
+                                                                      __half* __restrict__ act) {
+  const int ocg = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) & 3;     // warp-uniform channel group
+  const int lane = threadIdx.x & 31;
   const int qpr = (W + 3) >> 2;                        // pixel quads per row
   const long long nquads = (long long)nimg * H * qpr;
   const size_t hw = (size_t)H * W;
-  for (long long q = (long long)blockIdx.x * (kFirstThreads / 4) + ql; q < nquads; q += (long long)gridDim.x * (kFirstThreads / 4)) {
+  for (long long q0 = (long long)blockIdx.x * 32; q0 < nquads; q0 += (long long)gridDim.x * 32) {
+    const long long q = q0 + lane;
+    if (q >= nquads) continue;
     const int img = (int)(q / ((long long)H * qpr));
     const int r = (int)(q - (long long)img * H * qpr);
     const int y = r / qpr, x0 = (r - y * qpr) * 4;
@@ -75,10 +81,10 @@ __global__ void __launch_bounds__(kFirstThreads, 4) conv_first_kernel(int nimg, 
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int o = 0; o < 16; ++o) acc[p][o] = bs[ocg * 16 + o];
+      for (int o = 0; o < 16; ++o) acc[p][o] = wk.b[ocg * 16 + o];
 #pragma unroll
     for (int ci = 0; ci < CIN; ++ci) {
-      float v[3][6];            // 3x6 input window of this channel (only one channel live at a time)
+      float v[3][6];            // 3x6 input window of this channel
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy) {
         const int yy = y + dy - 1;
@@ -98,18 +104,12 @@ __global__ void __launch_bounds__(kFirstThreads, 4) conv_first_kernel(int nimg, 
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          const float4* wp = reinterpret_cast<const float4*>(&ws[((dy * 3 + dx) * CIN + ci) * 64 + ocg * 16]);
-          float w[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t = wp[j];
-            w[4 * j] = t.x; w[4 * j + 1] = t.y; w[4 * j + 2] = t.z; w[4 * j + 3] = t.w;
-          }
+          const float* wp = &wk.w[(dy * 3 + dx) * CIN + ci][ocg * 16];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             const float a = v[dy][p + dx];
 #pragma unroll
-            for (int o = 0; o < 16; ++o) acc[p][o] = fmaf(a, w[o], acc[p][o]);
+            for (int o = 0; o < 16; ++o) acc[p][o] = fmaf(a, wp[o], acc[p][o]);
           }
         }
     }
@@ -134,10 +134,13 @@ __global__ void __launch_bounds__(kFirstThreads, 4) conv_first_kernel(int nimg, 
 template <int CIN>
 cudaError_t launch_first_t(int nimg, int H, int W, const float* in, const DncnnLayerW& L, float slope, int clamp_in, __half* act_out,
                            cudaStream_t st) {
+  FirstW<CIN> wk;
+  std::memcpy(wk.w, L.w_first_host, sizeof(wk.w));
+  std::memcpy(wk.b, L.bias_host, sizeof(wk.b));
   const long long nquads = (long long)nimg * H * ((W + 3) / 4);
-  long long blocks = (nquads + kFirstThreads / 4 - 1) / (kFirstThreads / 4);
+  long long blocks = (nquads + 31) / 32;
   const int grid = (int)(blocks < 148 * 32 ? (blocks < 1 ? 1 : blocks) : 148 * 32);
-  conv_first_kernel<CIN><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, L.w_first, L.bias, slope, clamp_in, act_out);
+  conv_first_kernel<CIN><<<grid, kFirstThreads, 0, st>>>(nimg, H, W, in, wk, slope, clamp_in, act_out);
   return cudaGetLastError();
 }
 

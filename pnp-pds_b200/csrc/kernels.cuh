@@ -67,7 +67,8 @@ cudaError_t launch_l1ball(const Dims& d, const float* s_in, const float* t, cons
 // ---- dncnn_*.cu ---------------------------------------------------------------
 // Activations between layers: [img][2 (hi,lo)][H][W][64] fp16 ("NHWC hi/lo planes").
 struct DncnnLayerW {
-  const float* w_first;   // [9*Cin][64]     (k = tap*Cin + ci)          first layer
+  const float* w_first_host;  // HOST [9*Cin][64] (k = tap*Cin + ci): handed to the first-layer kernel by value (constant bank)
+  const float* bias_host;     // HOST [64] bias of the first layer
   const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
   const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][2 (hi,lo)][64 oc][64 ci] fp16, 128B-swizzled rows
   const float* w_last;    // [Cout][9][64 ci]                            last layer (SIMT engine)

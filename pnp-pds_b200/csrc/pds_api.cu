@@ -44,6 +44,7 @@ struct pds_handle_s {
   float slope = 0.f, res_sign = 1.f;
   int clamp = 1;
   std::vector<DncnnLayerW> layers;
+  std::vector<float> first_w_host, first_b_host;
   __half* act[2] = {nullptr, nullptr};
   int chunk = 1;
   TcPlan* tc = nullptr;
@@ -422,10 +423,10 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       for (int o = 0; o < co; ++o)
         for (int c = 0; c < ci; ++c)
           for (int tp = 0; tp < 9; ++tp) buf[((size_t)tp * ci + c) * 64 + o] = w[((size_t)o * ci + c) * 9 + tp];
-      float* dw = nullptr;
-      PDS_TRY(dev_alloc(h, &dw, buf.size()));
-      PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
-      L.w_first = dw;
+      h->first_w_host = buf;
+      h->first_b_host.assign(b, b + co);
+      L.w_first_host = h->first_w_host.data();
+      L.bias_host = h->first_b_host.data();
     } else if (l == depth - 1) {
       buf.assign((size_t)co * 9 * 64, 0.f);
       for (int o = 0; o < co; ++o)
