@@ -39,6 +39,10 @@ WORKLOADS = {
     "cfg2": dict(method="ours-B", deg_op="random_sampling", C=1, H=512, W=512, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
                  prm=dict(gamma1=1.0, gamma2=0.49, alpha_n=0.9, alpha_s=0.9, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.1,
                           poisson_alpha=300, r=0.8), poisson=False),
+    # cfg2 batched to HBM scale: the evidence workload for the fused pointwise prox kernels (north star item 2)
+    "cfg2b": dict(method="ours-B", deg_op="random_sampling", C=1, H=1024, W=1024, batch=64, arch="DnCNN_nobn_nch_1_nlev_0.01",
+                  prm=dict(gamma1=1.0, gamma2=0.49, alpha_n=0.9, alpha_s=0.9, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.1,
+                           poisson_alpha=300, r=0.8), poisson=False),
     "cfg3": dict(method="ours-C", deg_op="blur", C=1, H=256, W=256, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
                  prm=dict(gamma1=0.0006, gamma2=1 / 0.0006, alpha_n=0.9, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.0, sp_nl=0.0,
                           poisson_alpha=100, r=1.0), poisson=True),
@@ -333,8 +337,11 @@ def main():
         achieved = total_flop / (mid_ms * 1e-3) / 1e12 if mid_n else None
         dual_ms, dual_n = prof["dual"]
         prim_ms, prim_n = prof["primal"]
-        elem_bytes = (20 + 4) * n * B       # dual: read x+, x, t, b, x_true, write t (20 B + 4 B with PSNR)
-        prim_bytes = 12 * n * B
+        # algorithmic bytes per element: dual reads x+, x, t, b (+s+, s for ours-B) + x_true, writes t;
+        # primal reads x, t, writes u; +1 B per mask byte for random_sampling
+        mask_b = 1 if wl["deg_op"] == "random_sampling" else 0
+        elem_bytes = ((28 if mid == "B" else 20) + 4 + mask_b) * n * B
+        prim_bytes = (12 + mask_b) * n * B
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms_max / a.steps,
             higher_is_better=True, scaling="weak", vs_baseline=None,

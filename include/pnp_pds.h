@@ -40,7 +40,10 @@ enum {
   PDS_METHOD_B = 1,   /* B-Proposed / ours-B : iteration.py:53-58 */
   PDS_METHOD_C = 2,   /* C-Proposed / ours-C : iteration.py:59-63 */
   PDS_METHOD_FBS = 3, /* A-PnPFBS-DnCNN / comparisonA-1 : iteration.py:71-73 */
-  PDS_METHOD_RED = 4  /* A-RED-DnCNN / comparisonA-6 : iteration.py:100-105 */
+  PDS_METHOD_RED = 4, /* A-RED-DnCNN / comparisonA-6 : iteration.py:100-105 */
+  PDS_METHOD_ADMM_B2 = 5, /* comparisonB-2 : iteration.py:127-132 + algorithm/admm.py:30-44 */
+  PDS_METHOD_ADMM_C = 6,  /* C-PnPADMM-DnCNN / comparisonC-2 : iteration.py:161-165 + admm.py:4-16 */
+  PDS_METHOD_RED_C = 7    /* C-RED-DnCNN / comparisonC-3 : iteration.py:166-172 + admm.py:4-28 */
 };
 
 /* engine used for the 64->64 channel layers of the denoiser */
@@ -98,6 +101,8 @@ int pds_set_blur_kernel(pds_handle_t h, const double* kernel_host, int l);
 int pds_set_mask(pds_handle_t h, const uint8_t* mask_host);
 /* n == batch, or n == 1 to broadcast */
 int pds_set_item_params(pds_handle_t h, const pds_item_params_t* params_host, int n);
+/* inner trip counts and step size of the ADMM cross-check loops: m1, m2, gammaInADMMStep1 (iteration.py:10) */
+int pds_set_admm(pds_handle_t h, int m1, int m2, float gamma_step1);
 /* PDSW weight blob (models/weights.py) — replaces Denoiser.__init__/load_network (denoiser.py:9-32) */
 int pds_load_dncnn(pds_handle_t h, const void* blob_host, size_t nbytes);
 

@@ -38,11 +38,24 @@ cudaError_t launch_scale_by_sigma(const Dims& d, const float* t, const ItemParam
 cudaError_t launch_diff_norm2(const Dims& d, const float* x, const float* c, double* acc /*[B]*/, cudaStream_t st);
 cudaError_t launch_proj_l2_apply(const Dims& d, const float* x, const float* c, float eps, const double* acc, float* out,
                                  cudaStream_t st);
+cudaError_t launch_proj_l2_items(const Dims& d, const float* x, const float* c, const ItemParams* prm, const double* acc, float* out,
+                                 cudaStream_t st);
 cudaError_t launch_prox_gkl(const Dims& d, const float* x, const float* x0, float gamma, float alpha, float* out,
                             cudaStream_t st);
 // metrics for methods without a dual kernel: fills SUM_DX2, SUM_X2, SUM_ERR2
 cudaError_t launch_metrics(const Dims& d, const float* xn, const float* x, const float* xtrue, double* sums_cur,
                            cudaStream_t st);
+// out[i] = sum_k coef[b][k] * in[k][i] per item b (ADMM cross-check loops)
+struct LinArgs {
+  Dims d;
+  const float* in[6];
+  float* out;
+  const float* coef;   // device [B][6]
+  int nterms;
+};
+cudaError_t launch_lincomb(const LinArgs& a, cudaStream_t st);
+cudaError_t launch_ratio(const Dims& d, const float* num, const float* den, const ItemParams* prm, float* out, cudaStream_t st);
+cudaError_t launch_fill(size_t n, float v, float* out, cudaStream_t st);
 // out = a*p + b*q + c*r   (r, q may be null)
 cudaError_t launch_axpbypcz(size_t n, float a, const float* p, float b, const float* q, float c, const float* r, float* out,
                             cudaStream_t st);

@@ -27,6 +27,16 @@ struct pds_handle_s {
   float* obs = nullptr;
   float* xtrue = nullptr;
   float* tmp[2] = {nullptr, nullptr};
+  // ADMM cross-check loops (algorithm/admm.py): z, d, work buffers, adj_phi(ones), coefficient table
+  float* zbuf = nullptr;
+  float* dbuf = nullptr;
+  float* wrk[3] = {nullptr, nullptr, nullptr};
+  float* ones_adj = nullptr;
+  float* coef = nullptr;          // device [8 combos][B][6]
+  bool coef_ready = false;
+  std::vector<ItemParams> prm_host;
+  int m1 = 15, m2 = 15;
+  float gamma_step1 = 0.1f;
   bool have_true = false, have_problem = false;
   int cur = 0, scur = 0, iter = 0;
   uint8_t* mask = nullptr;
@@ -259,6 +269,143 @@ int fbs_red_iteration(pds_handle_s* h, cudaStream_t st) {
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// ADMM cross-check loops (algorithm/admm.py, iteration.py:127-132,161-172).
+// Compositions of the operators above plus per-item linear combinations (launch_lincomb).
+// ---------------------------------------------------------------------------------------------
+enum { CB_R = 0, CB_XIN = 1, CB_S = 2, CB_V = 3, CB_Y = 4, CC_X = 0, CC_V = 1, CC_D = 2, CC_Z = 3 };
+
+int build_coefs(pds_handle_s* h) {
+  const int B = h->d.B;
+  std::vector<float> c((size_t)8 * B * 6, 0.f);
+  auto at = [&](int combo, int b) { return &c[((size_t)combo * B + b) * 6]; };
+  for (int b = 0; b < B; ++b) {
+    const ItemParams& p = h->prm_host[b];
+    if (h->cfg.method == PDS_METHOD_ADMM_B2) {
+      const float ig = 1.f / p.g1;
+      float* q;
+      q = at(CB_R, b);   q[0] = 1.f; q[1] = 1.f; q[2] = -1.f; q[3] = 1.f;          // Phi x + s - z + y          (admm.py:34,42)
+      q = at(CB_XIN, b); q[0] = 1.f; q[1] = -ig;                                    // x - (1/g1) Phi^T r          (admm.py:34)
+      q = at(CB_S, b);   q[0] = 1.f - ig; q[1] = -ig; q[2] = ig; q[3] = -ig;         // s - (1/g1)(Phi x + s - z + y) (admm.py:42)
+      q = at(CB_V, b);   q[0] = 1.f; q[1] = 1.f; q[2] = 1.f;                        // Phi x + s + y               (iteration.py:131)
+      q = at(CB_Y, b);   q[0] = 1.f; q[1] = 1.f; q[2] = 1.f; q[3] = -1.f;           // y + Phi x + s - z           (iteration.py:132)
+    } else {
+      const float g = h->gamma_step1, gl = g * p.lam, ga = g / p.alpha;
+      float* q;
+      q = at(CC_X, b); q[0] = 1.f - gl; q[1] = ga; q[2] = -ga; q[3] = gl; q[4] = -gl;  // x - g*grad                (admm.py:12-13)
+      q = at(CC_V, b); q[0] = 1.f; q[1] = 1.f;                                         // x + d                     (iteration.py:163)
+      q = at(CC_D, b); q[0] = 1.f; q[1] = 1.f; q[2] = -1.f;                            // d + x - z                 (iteration.py:164)
+      q = at(CC_Z, b); q[0] = p.g1 / (p.lam + p.g1); q[1] = p.lam / (p.lam + p.g1);    // (g1 D(z) + lam z*)/(lam+g1) (admm.py:27)
+    }
+  }
+  PDS_CUDA_OK(cudaMemcpy(h->coef, c.data(), c.size() * sizeof(float), cudaMemcpyHostToDevice));
+  h->coef_ready = true;
+  return 0;
+}
+
+int lin(pds_handle_s* h, int combo, int nterms, float* out, const float* i0, const float* i1, const float* i2, const float* i3,
+        const float* i4, cudaStream_t st) {
+  LinArgs a{};
+  a.d = h->d;
+  a.in[0] = i0; a.in[1] = i1; a.in[2] = i2; a.in[3] = i3; a.in[4] = i4; a.in[5] = nullptr;
+  a.out = out;
+  a.coef = h->coef + (size_t)combo * h->d.B * 6;
+  a.nterms = nterms;
+  PDS_LAUNCH(h, launch_lincomb(a, st));
+  return 0;
+}
+
+int phi_into(pds_handle_s* h, bool adjoint, const float* in, float* out, cudaStream_t st) { return apply_phi(h, adjoint, in, out, st); }
+
+// comparisonB-2 (iteration.py:127-132 + admm.py:30-44).  State: x (xbuf), s (sbuf), z, y (= t, stored directly).
+int admm_b2_iteration(pds_handle_s* h, cudaStream_t st) {
+  const size_t n = total_elems(h);
+  float* x_prev = h->xbuf[h->cur];
+  float* x = h->xbuf[h->cur ^ 1];
+  float* s = h->sbuf[h->scur];
+  float* y = h->t;
+  float* z = h->zbuf;
+  float *w0 = h->wrk[0], *w1 = h->wrk[1], *w2 = h->wrk[2];
+  // x-step: m1 trips from x = 1
+  PDS_LAUNCH(h, launch_fill(n, 1.f, x, st));
+  for (int i = 0; i < h->m1; ++i) {
+    PDS_TRY(phi_into(h, false, x, w0, st));
+    PDS_TRY(lin(h, CB_R, 4, w0, w0, s, z, y, nullptr, st));
+    PDS_TRY(phi_into(h, true, w0, w1, st));
+    PDS_TRY(lin(h, CB_XIN, 2, w2, x, w1, nullptr, nullptr, nullptr, st));
+    PDS_TRY(run_dncnn(h, w2, x, st));
+  }
+  // s-step: m2 trips from s = 1 (Phi x fixed)
+  PDS_TRY(phi_into(h, false, x, w0, st));
+  float* sn = h->sbuf[h->scur ^ 1];
+  PDS_LAUNCH(h, launch_fill(n, 1.f, w1, st));
+  for (int i = 0; i < h->m2; ++i) {
+    PDS_TRY(lin(h, CB_S, 4, w2, w1, w0, z, y, nullptr, st));
+    PDS_LAUNCH(h, launch_l1ball(h->d, w2, nullptr, h->prm, nullptr, -1.f, w1, nullptr, st));
+  }
+  PDS_CUDA_OK(cudaMemcpyAsync(sn, w1, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // z = P_l2(Phi x + s + y) ; y += Phi x + s - z
+  PDS_TRY(lin(h, CB_V, 3, w2, w0, sn, y, nullptr, nullptr, st));
+  PDS_CUDA_OK(cudaMemsetAsync(h->scratch, 0, (size_t)h->d.B * sizeof(double), st));
+  PDS_LAUNCH(h, launch_diff_norm2(h->d, w2, h->obs, h->scratch, st));
+  PDS_LAUNCH(h, launch_proj_l2_items(h->d, w2, h->obs, h->prm, h->scratch, z, st));
+  PDS_TRY(lin(h, CB_Y, 4, y, y, w0, sn, z, nullptr, st));
+  const size_t row = (size_t)h->d.B * NSUM;
+  PDS_LAUNCH(h, launch_metrics(h->d, x, x_prev, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  h->cur ^= 1;
+  h->scur ^= 1;
+  h->iter++;
+  return 0;
+}
+
+// C-PnPADMM-DnCNN (iteration.py:161-165) and C-RED-DnCNN (iteration.py:166-172) + admm.py:4-28.
+int admm_c_iteration(pds_handle_s* h, cudaStream_t st) {
+  const size_t n = total_elems(h);
+  float* x_prev = h->xbuf[h->cur];
+  float* x = h->xbuf[h->cur ^ 1];
+  float* z = h->zbuf;
+  float* dd = h->dbuf;
+  float *w0 = h->wrk[0], *w1 = h->wrk[1], *w2 = h->wrk[2];
+  PDS_LAUNCH(h, launch_fill(n, 1.f, x, st));
+  for (int i = 0; i < h->m1; ++i) {
+    PDS_TRY(phi_into(h, false, x, w0, st));
+    PDS_LAUNCH(h, launch_ratio(h->d, h->obs, w0, h->prm, w0, st));            // y / (alpha Phi x)
+    PDS_TRY(phi_into(h, true, w0, w1, st));
+    PDS_TRY(lin(h, CC_X, 5, x, x, w1, h->ones_adj, z, dd, st));
+  }
+  if (h->cfg.method == PDS_METHOD_ADMM_C) {
+    PDS_TRY(lin(h, CC_V, 2, w2, x, dd, nullptr, nullptr, nullptr, st));
+    PDS_TRY(run_dncnn(h, w2, z, st));
+  } else {
+    PDS_TRY(lin(h, CC_V, 2, w2, x, dd, nullptr, nullptr, nullptr, st));        // z* = x + d
+    for (int i = 0; i < h->m2; ++i) {
+      PDS_TRY(run_dncnn(h, z, w0, st));
+      PDS_TRY(lin(h, CC_Z, 2, z, w0, w2, nullptr, nullptr, nullptr, st));
+    }
+  }
+  PDS_TRY(lin(h, CC_D, 3, dd, dd, x, z, nullptr, nullptr, st));
+  const size_t row = (size_t)h->d.B * NSUM;
+  PDS_LAUNCH(h, launch_metrics(h->d, x, x_prev, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  h->cur ^= 1;
+  h->iter++;
+  return 0;
+}
+
+int admm_prepare(pds_handle_s* h, cudaStream_t st) {
+  if (!h->coef_ready) PDS_TRY(build_coefs(h));
+  if (h->iter == 0) {
+    const size_t nb = total_elems(h) * sizeof(float);
+    PDS_CUDA_OK(cudaMemsetAsync(h->zbuf, 0, nb, st));
+    PDS_CUDA_OK(cudaMemsetAsync(h->dbuf, 0, nb, st));
+    if (h->cfg.method != PDS_METHOD_ADMM_B2) {
+      PDS_LAUNCH(h, launch_fill(total_elems(h), 1.f, h->wrk[2], st));
+      PDS_TRY(phi_into(h, true, h->wrk[2], h->ones_adj, st));               // adj_phi(ones)  (admm.py:12)
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -279,7 +426,7 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   PDS_REQUIRE(cfg && out, "null argument");
   PDS_REQUIRE(cfg->batch >= 1 && cfg->height >= 1 && cfg->width >= 1, "bad shape");
   PDS_REQUIRE(cfg->channels == 1 || cfg->channels == 3, "channels must be 1 or 3 (reference ch)");
-  PDS_REQUIRE(cfg->method >= PDS_METHOD_A && cfg->method <= PDS_METHOD_RED, "unknown method");
+  PDS_REQUIRE(cfg->method >= PDS_METHOD_A && cfg->method <= PDS_METHOD_RED_C, "unknown method");
   PDS_REQUIRE(cfg->deg_op >= PDS_OP_ID && cfg->deg_op <= PDS_OP_RANDOM_SAMPLING, "unknown deg_op");
   PDS_REQUIRE(cfg->max_iter >= 1, "max_iter must be >= 1");
   PDS_REQUIRE((long long)cfg->batch * cfg->channels <= 65535, "batch*channels exceeds the grid limit");
@@ -302,6 +449,11 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   A(&h->obs, n); A(&h->xtrue, n);
   if (cfg->method == PDS_METHOD_B) { A(&h->sbuf[0], n); A(&h->sbuf[1], n); }
   if (cfg->method == PDS_METHOD_FBS || cfg->method == PDS_METHOD_RED) { A(&h->tmp[0], n); A(&h->tmp[1], n); }
+  if (cfg->method >= PDS_METHOD_ADMM_B2) {
+    A(&h->zbuf, n); A(&h->dbuf, n); A(&h->wrk[0], n); A(&h->wrk[1], n); A(&h->wrk[2], n); A(&h->ones_adj, n);
+    A(&h->coef, (size_t)8 * cfg->batch * 6);
+    if (cfg->method == PDS_METHOD_ADMM_B2 && !h->sbuf[0]) { A(&h->sbuf[0], n); A(&h->sbuf[1], n); }
+  }
   A(&h->mask, (size_t)h->d.hw);
   A(&h->prm, (size_t)cfg->batch);
   A(&h->sums, (size_t)cfg->max_iter * cfg->batch * NSUM);
@@ -374,6 +526,8 @@ int pds_set_item_params(pds_handle_t h, const pds_item_params_t* p, int n) {
     v[b] = ItemParams{q.gamma1, q.gamma2, q.epsilon, q.eta, q.lambda, q.alpha};
   }
   PDS_CUDA_OK(cudaMemcpy(h->prm, v.data(), v.size() * sizeof(ItemParams), cudaMemcpyHostToDevice));
+  h->prm_host = v;
+  h->coef_ready = false;
   h->have_params = true;
   return 0;
 }
@@ -567,8 +721,23 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   for (int i = 0; i < n_iter; ++i) {
     if (h->cfg.method <= PDS_METHOD_C) PDS_TRY(pds_iteration(h, st));
-    else PDS_TRY(fbs_red_iteration(h, st));
+    else if (h->cfg.method <= PDS_METHOD_RED) PDS_TRY(fbs_red_iteration(h, st));
+    else {
+      PDS_TRY(admm_prepare(h, st));
+      if (h->cfg.method == PDS_METHOD_ADMM_B2) PDS_TRY(admm_b2_iteration(h, st));
+      else PDS_TRY(admm_c_iteration(h, st));
+    }
   }
+  return 0;
+}
+
+int pds_set_admm(pds_handle_t h, int m1, int m2, float gamma_step1) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(m1 >= 0 && m2 >= 0, "m1, m2 must be >= 0");
+  h->m1 = m1;
+  h->m2 = m2;
+  h->gamma_step1 = gamma_step1;
+  h->coef_ready = false;
   return 0;
 }
 
@@ -587,7 +756,8 @@ int pds_get_state(pds_handle_t h, float* x, float* s, float* y, pds_stream_t str
   if (y) {
     const size_t row = (size_t)h->d.B * NSUM;
     const double* sums = h->iter > 0 ? h->sums + (size_t)(h->iter - 1) * row : nullptr;
-    PDS_LAUNCH(h, launch_scale_by_sigma(h->d, h->t, h->prm, sums, h->cfg.method, y, st));
+    if (h->cfg.method <= PDS_METHOD_B) PDS_LAUNCH(h, launch_scale_by_sigma(h->d, h->t, h->prm, sums, h->cfg.method, y, st));
+    else PDS_CUDA_OK(cudaMemcpyAsync(y, h->t, nb, cudaMemcpyDeviceToDevice, st));
   }
   return 0;
 }

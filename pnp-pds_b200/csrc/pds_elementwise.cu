@@ -212,6 +212,28 @@ __global__ void __launch_bounds__(kThreads) proj_l2_apply_kernel(Dims d, const f
   }
 }
 
+// same with the radius taken per item from prm[b].eps (ADMM loops)
+template <int V>
+__global__ void __launch_bounds__(kThreads) proj_l2_items_kernel(Dims d, const float* x, const float* __restrict__ c, const ItemParams* prm,
+                                                                 const double* __restrict__ acc, float* out) {
+  const size_t base = (size_t)blockIdx.y * d.n;
+  const float eps = prm[blockIdx.y].eps;
+  const float nrm = (float)sqrt(acc[blockIdx.y]);
+  const bool outside = nrm > eps;
+  const float sc = outside ? eps / nrm : 1.f;
+  const int nv = d.n / V;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nv; i += gridDim.x * kThreads) {
+    float a[V], q[V];
+    load_rw<V>(x, base + (size_t)i * V, a);
+    load<V>(c, base + (size_t)i * V, q);
+    if (outside) {
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] = fmaf(sc, a[k] - q[k], q[k]);
+    }
+    store<V>(out, base + (size_t)i * V, a);
+  }
+}
+
 // operators.py:114-115, stable for x - gamma*alpha << 0.
 template <int V>
 __global__ void __launch_bounds__(kThreads) prox_gkl_kernel(Dims d, const float* __restrict__ x, const float* __restrict__ x0,
@@ -269,6 +291,53 @@ __global__ void __launch_bounds__(kThreads) axpbypcz_kernel(size_t n, float a, c
     if (r) v = fmaf(c, r[i], v);
     out[i] = v;
   }
+}
+
+// out[i] = sum_k coef[b][k] * in_k[i]   (k < nterms <= 6); out may alias an input (same index only)
+template <int V>
+__global__ void __launch_bounds__(kThreads) lincomb_kernel(LinArgs a) {
+  const int b = blockIdx.y;
+  float c[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) c[k] = (k < a.nterms) ? a.coef[(size_t)b * 6 + k] : 0.f;
+  const size_t base = (size_t)b * a.d.n;
+  const int nv = a.d.n / V;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nv; i += gridDim.x * kThreads) {
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (k < a.nterms) {
+        float v[V];
+        load_rw<V>(a.in[k], base + (size_t)i * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = fmaf(c[k], v[j], acc[j]);
+      }
+    }
+    store<V>(a.out, base + (size_t)i * V, acc);
+  }
+}
+
+// out = num / (alpha_b * den)      (admm.py:12: y / (poisson_alpha * phi(x)))
+template <int V>
+__global__ void __launch_bounds__(kThreads) ratio_kernel(Dims d, const float* num, const float* den, const ItemParams* prm, float* out) {
+  const int b = blockIdx.y;
+  const float alpha = prm[b].alpha;
+  const size_t base = (size_t)b * d.n;
+  const int nv = d.n / V;
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < nv; i += gridDim.x * kThreads) {
+    float p[V], q[V];
+    load_rw<V>(num, base + (size_t)i * V, p);
+    load_rw<V>(den, base + (size_t)i * V, q);
+#pragma unroll
+    for (int j = 0; j < V; ++j) p[j] = p[j] / (alpha * q[j]);
+    store<V>(out, base + (size_t)i * V, p);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) fill_kernel(size_t n, float v, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (size_t)gridDim.x * kThreads) out[i] = v;
 }
 
 inline bool vec4_ok(const Dims& d) { return (d.n % 4 == 0) && (d.hw % 4 == 0); }
@@ -355,6 +424,13 @@ cudaError_t launch_proj_l2_apply(const Dims& d, const float* x, const float* c, 
   return cudaGetLastError();
 }
 
+cudaError_t launch_proj_l2_items(const Dims& d, const float* x, const float* c, const ItemParams* prm, const double* acc, float* out,
+                                 cudaStream_t st) {
+  PDS_DISPATCH_V(d, (proj_l2_items_kernel<4><<<grid_for(d, 4), kThreads, 0, st>>>(d, x, c, prm, acc, out)),
+                 (proj_l2_items_kernel<1><<<grid_for(d, 1), kThreads, 0, st>>>(d, x, c, prm, acc, out)));
+  return cudaGetLastError();
+}
+
 cudaError_t launch_prox_gkl(const Dims& d, const float* x, const float* x0, float gamma, float alpha, float* out, cudaStream_t st) {
   PDS_DISPATCH_V(d, (prox_gkl_kernel<4><<<grid_for(d, 4), kThreads, 0, st>>>(d, x, x0, gamma, alpha, out)),
                  (prox_gkl_kernel<1><<<grid_for(d, 1), kThreads, 0, st>>>(d, x, x0, gamma, alpha, out)));
@@ -364,6 +440,24 @@ cudaError_t launch_prox_gkl(const Dims& d, const float* x, const float* x0, floa
 cudaError_t launch_metrics(const Dims& d, const float* xn, const float* x, const float* xtrue, double* sums_cur, cudaStream_t st) {
   PDS_DISPATCH_V(d, (metrics_kernel<4><<<grid_for(d, 4), kThreads, 0, st>>>(d, xn, x, xtrue, sums_cur)),
                  (metrics_kernel<1><<<grid_for(d, 1), kThreads, 0, st>>>(d, xn, x, xtrue, sums_cur)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_lincomb(const LinArgs& a, cudaStream_t st) {
+  PDS_DISPATCH_V(a.d, (lincomb_kernel<4><<<grid_for(a.d, 4), kThreads, 0, st>>>(a)), (lincomb_kernel<1><<<grid_for(a.d, 1), kThreads, 0, st>>>(a)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ratio(const Dims& d, const float* num, const float* den, const ItemParams* prm, float* out, cudaStream_t st) {
+  PDS_DISPATCH_V(d, (ratio_kernel<4><<<grid_for(d, 4), kThreads, 0, st>>>(d, num, den, prm, out)),
+                 (ratio_kernel<1><<<grid_for(d, 1), kThreads, 0, st>>>(d, num, den, prm, out)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill(size_t n, float v, float* out, cudaStream_t st) {
+  size_t blocks = (n + (size_t)kThreads * 4 - 1) / ((size_t)kThreads * 4);
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+  fill_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(n, v, out);
   return cudaGetLastError();
 }
 

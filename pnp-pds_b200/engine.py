@@ -27,6 +27,8 @@ METHOD_ALIASES = {
 RESIDENT_METHODS = {
     "A-Proposed": "A", "B-Proposed": "B", "C-Proposed": "C",
     "A-PnPFBS-DnCNN": "FBS", "A-RED-DnCNN": "RED",
+    # ADMM cross-checks (algorithm/admm.py)
+    "comparisonB-2": "ADMM_B2", "C-PnPADMM-DnCNN": "ADMM_C", "C-RED-DnCNN": "RED_C",
     # the "unstable" KAIR variants run the same PDS loop with a different denoiser epilogue
     "A-PnPPDS-unstable-DnCNN": "A", "C-PnP-unstable-DnCNN": "C",
 }
@@ -121,6 +123,10 @@ class Engine:
             arr[i] = PdsItemParams(float(p.get("gamma1", 1.0)), float(p.get("gamma2", 1.0)), float(p.get("epsilon", 0.0)),
                                    float(p.get("eta", 0.0)), float(p.get("lam", 1.0)), float(p.get("alpha", 1.0)))
         _lib.check(self.lib.pds_set_item_params(self._h, arr, len(params)))
+
+    def set_admm(self, m1: int, m2: int, gamma_step1: float):
+        """m1, m2, gammaInADMMStep1 of iteration.test_iter (inner trip counts / step of algorithm/admm.py)."""
+        _lib.check(self.lib.pds_set_admm(self._h, int(m1), int(m2), float(gamma_step1)))
 
     def load_dncnn(self, weights: DnCNNWeights | bytes):
         blob = weights.to_blob() if isinstance(weights, DnCNNWeights) else bytes(weights)

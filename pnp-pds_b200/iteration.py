@@ -20,7 +20,7 @@ _OUT_OF_SCOPE = {
     "A-PnPPDS-BM3D", "A-PnPFBS-BM3D", "comparisonB-1", "C-PnPPDS-BM3D",      # need the bm3d wheel (CPU-only algorithm)
     "A-PDS-TV", "A-FBS-TV", "comparisonB-3",                                   # TV baselines, no denoiser
 }
-_NOT_RESIDENT_YET = {"comparisonB-2", "C-PnPADMM-DnCNN", "C-RED-DnCNN"}     # ADMM cross-checks
+_NO_REFERENCE_BEHAVIOUR = {"comparisonB-4", "comparisonB-5"}   # the reference dies with UnboundLocalError (iteration.py:40,143,148)
 
 
 def _check_ops(phi, adj_phi):
@@ -39,21 +39,22 @@ def item_params(method_id: str, n: int, gamma1, gamma2, alpha_s, alpha_n, myLamb
     to proj_l2_ball (iteration.py:52) so epsilon uses r = 1; B-Proposed passes r to both projections
     (iteration.py:56,58)."""
     r_l2 = r if method_id == "B" else 1.0
+    r_l1 = 1.0 if method_id == "ADMM_B2" else r       # comparisonB-2 calls both projections without r (iteration.py:131, admm.py:43)
     return dict(gamma1=gamma1, gamma2=gamma2, epsilon=l2_ball_radius(n, alpha_n, gaussian_nl, sp_nl, r_l2),
-                eta=l1_ball_radius(n, alpha_s, sp_nl, r), lam=myLambda, alpha=poisson_alpha)
+                eta=l1_ball_radius(n, alpha_s, sp_nl, r_l1), lam=myLambda, alpha=poisson_alpha)
 
 
 def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict, path_prox, max_iter: int,
               method: str = "A-Proposed", ch: int = 3, conv_engine: str = "tcgen05", device=None, ssim: str = "final",
-              denoiser_chunk: int = 0):
+              denoiser_chunk: int = 0, m1: int = 15, m2: int = 15, gammaInADMMStep1: float = 0.1):
     """B restorations at once.  x_0, x_obsrv, x_true: (B,H,W) for ch=1 or (B,3,H,W).
     params: dict(s) with gamma1, gamma2, alpha_s, alpha_n, myLambda, gaussian_nl, sp_nl, poisson_alpha, r.
     Returns dict(x, s, c, psnr, ssim, time_per_iter, traces, launches)."""
     name = canonical_method(method)
     if name in _OUT_OF_SCOPE:
         raise ValueError(f"method {method!r} is outside the B200 hot path (BM3D / TV baselines, see DESIGN.md)")
-    if name in _NOT_RESIDENT_YET:
-        raise NotImplementedError(f"method {method!r}: ADMM cross-check loops are not resident yet (DESIGN.md, next rows)")
+    if name in _NO_REFERENCE_BEHAVIOUR:
+        raise NotImplementedError(f"method {method!r} cannot run in the reference either (denoiser_J is never constructed for it)")
     if name not in RESIDENT_METHODS:
         raise ValueError(f"Unknown method: {method}")
     mid = RESIDENT_METHODS[name]
@@ -84,6 +85,8 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         elif kind == "random_sampling":
             eng.set_mask(sampling_mask(H, W, phi.r))
         eng.set_params(items)
+        if mid in ("ADMM_B2", "ADMM_C", "RED_C"):
+            eng.set_admm(m1, m2, gammaInADMMStep1)
         eng.load_dncnn(weights)
         import torch
         t0 = time.perf_counter()
@@ -119,7 +122,7 @@ def test_iter(x_0, x_obsrv, x_true, phi, adj_phi, gamma1, gamma2, alpha_s, alpha
              sp_nl=sp_nl, poisson_alpha=poisson_alpha, r=r)
     x_0 = np.asarray(x_0)
     res = run_batch(x_0[None], np.asarray(x_obsrv)[None], None if x_true is None else np.asarray(x_true)[None], phi, adj_phi,
-                    p, path_prox, max_iter, method, ch)
+                    p, path_prox, max_iter, method, ch, m1=m1, m2=m2, gammaInADMMStep1=gammaInADMMStep1)
     return (res["x"][0], res["s"][0].astype(np.float64) + 0.5, res["c"][:, 0], res["psnr"][:, 0], res["ssim"][:, 0],
             res["time_per_iter"])
 

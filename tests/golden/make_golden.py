@@ -171,6 +171,9 @@ LOOP_CASES = [
     dict(tag="CADMM_blur_g", method="C-PnPADMM-DnCNN", deg_op="blur", ch=1, hw=(32, 32), gaussian_nl=0.0, sp_nl=0.0,
          poisson_noise=True, poisson_alpha=300, gamma1=0.02, gamma2=1.0, myLambda=0.025, m1=10, m2=3,
          gammaInADMMStep1=1.0, alpha_n=0.9, alpha_s=0.95, r=1.0, iters=5),
+    dict(tag="CRED_blur_g", method="C-RED-DnCNN", deg_op="blur", ch=1, hw=(32, 32), gaussian_nl=0.0, sp_nl=0.0,
+         poisson_noise=True, poisson_alpha=300, gamma1=0.02, gamma2=1.0, myLambda=0.03, m1=8, m2=3,
+         gammaInADMMStep1=10.0, alpha_n=0.9, alpha_s=0.95, r=1.0, iters=4),
 ]
 
 LONG_CASES = [

@@ -24,7 +24,8 @@ def _run(g, assets, tag, n_iter, engine="tcgen05"):
                myLambda=case.get("myLambda", 1.0), gaussian_nl=case["gaussian_nl"], sp_nl=case["sp_nl"],
                poisson_alpha=case.get("poisson_alpha", 300), r=case.get("r", 1.0))
     res = iteration.run_batch(g[f"{tag}/x0"][None], g[f"{tag}/obs"][None], g[f"{tag}/x_true"][None], phi, adj, prm,
-                              weights_path(arch), n_iter, case["method"], case["ch"], conv_engine=engine)
+                              weights_path(arch), n_iter, case["method"], case["ch"], conv_engine=engine,
+                              m1=case.get("m1", 15), m2=case.get("m2", 15), gammaInADMMStep1=case.get("gammaInADMMStep1", 0.1))
     return case, res
 
 
@@ -45,6 +46,22 @@ def test_short_traces(g_loops, assets, tag, engine):
         assert np.max(np.abs(res["s"][0] + 0.5 - ref_s)) < 1e-4, (tag, n)
     assert np.allclose(res["c"][:, 0], g_loops[f"{tag}/c"], rtol=5e-3, atol=2e-6), tag
     assert np.max(np.abs(res["psnr"][:, 0] - g_loops[f"{tag}/psnr"])) < DPSNR_GATE, tag
+
+
+@pytest.mark.parametrize("tag", ["B2_blur_g", "CADMM_blur_g", "CRED_blur_g"])
+def test_admm_crosschecks(g_loops, assets, tag):
+    """comparisonB-2 / C-PnPADMM-DnCNN / C-RED-DnCNN (algorithm/admm.py) as resident loops vs the reference's traces."""
+    case = json.loads(str(g_loops[f"{tag}/case"]))
+    for n in (1, 2, case["iters"]):
+        _, res = _run(g_loops, assets, tag, n)
+        ref_x = g_loops[f"{tag}/x_{n}"]
+        e = rel_l2(res["x"][0], ref_x)
+        print(f"{tag} n={n}: rel_l2(x)={e:.2e} max_abs={np.max(np.abs(res['x'][0] - ref_x)):.2e}")
+        # the ADMM cases sit on near-zero iterates early on: relative OR absolute fp32-level agreement
+        assert e < REL_L2_GATE or np.max(np.abs(res["x"][0] - ref_x)) < 5e-6, (tag, n)
+        assert np.max(np.abs(res["s"][0] + 0.5 - g_loops[f"{tag}/s05_{n}"])) < 1e-4
+    assert np.allclose(res["c"][:, 0], g_loops[f"{tag}/c"], rtol=5e-3, atol=2e-6)
+    assert np.max(np.abs(res["psnr"][:, 0] - g_loops[f"{tag}/psnr"])) < DPSNR_GATE
 
 
 LONG = ["LONG_A_blur_g", "LONG_C_blur_g", "LONG_B_rs_g", "LONG_A_blur_c"]
@@ -79,6 +96,8 @@ def test_test_iter_signature_and_errors(g_loops, assets):
         iteration.test_iter(*args, "no-such-method", 1, 1.0)
     with pytest.raises(ValueError):
         iteration.test_iter(*args, "A-PnPPDS-BM3D", 1, 1.0)
+    with pytest.raises(NotImplementedError):
+        iteration.test_iter(*args, "comparisonB-5", 1, 1.0)      # dies in the reference too (UnboundLocalError)
     with pytest.raises(TypeError):
         iteration.test_iter(*args[:3], lambda z: z, lambda z: z, *args[5:], "A-Proposed", 1, 1.0)
 
