@@ -365,6 +365,253 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// 2-CTA variant of the body layer (cta_group::2): a cluster of two CTAs works on two pixel tiles at
+// once as ONE M=256 UMMA issued by CTA 0.  The B operand (weights) is split between the two CTAs'
+// shared memories, so every SM reads only half of B per MMA and keeps only half of the weight image
+// (72 KB instead of 144 KB): the SS-mode MMA is bound by shared-memory operand reads, and this takes
+// the per-tile operand traffic from 504 KB to 396 KB while freeing room for a 5-slot plane ring.
+//   B rows (N = 128, hi plane):  [ w_hi[0:32] ; w_lo[0:32] | w_hi[32:64] ; w_lo[32:64] ]   (CTA 0 | CTA 1)
+//   B rows (N = 64,  lo plane):  [ w_hi[0:32]              | w_hi[32:64]             ]   (first 32 rows of each half)
+//   accumulator columns per stage: [0,32) hh oc<32, [32,64) hl oc<32, [64,96) hh oc>=32, [96,128) hl oc>=32,
+//                                  [128,192) lo-plane a_lo*w_hi for oc 0..63
+// ---------------------------------------------------------------------------------------------
+namespace two {
+constexpr uint32_t kWHalf = 9 * 64 * 128;             // 73728: per-CTA weight image
+constexpr int kSlots2 = 5;
+constexpr uint32_t kOffA2 = kWHalf, kOffBar2 = kOffA2 + kSlots2 * kPlaneSlot;
+constexpr uint32_t kOffBias2 = kOffBar2 + 192, kSmemBytes2 = kOffBias2 + 256 + 1024;
+constexpr uint32_t kAccCols2 = 192, kTmemCols2 = 512;
+constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16, M=256
+constexpr uint32_t kIdescN128 = kIdescBase2 | ((128u >> 3) << 17), kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+template <bool HI_PLANE>
+__device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
+  constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);
+  constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
+      const uint32_t bo = (uint32_t)(tap * 8192 + k * 32) >> 4;
+      if (HI_PLANE) umma_f16_2sm(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN128, (tap == 0 && k == 0) ? 0u : 1u);
+      else umma_f16_2sm(d_tmem + 128u, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, (tap == 0 && k == 0) ? 0u : 1u);
+    }
+  }
+}
+
+// 32 channels [c0, c0+32) of one pixel from three accumulator pieces.
+__device__ __forceinline__ void store_32ch(__half* dst_hi, __half* dst_lo, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
+                                           const uint32_t (&d2)[32], const float* bias_s, int c0, float slope) {
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = q * 16 + 2 * k;
+      const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
+      float v0 = ((__uint_as_float(d0[c]) + __uint_as_float(d1[c])) + __uint_as_float(d2[c])) + b.x;
+      float v1 = ((__uint_as_float(d0[c + 1]) + __uint_as_float(d1[c + 1])) + __uint_as_float(d2[c + 1])) + b.y;
+      v0 = fmaxf(v0, v0 * slope);
+      v1 = fmaxf(v1, v1 * slope);
+      const __half2 hh = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+      hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    st_global_256(dst_hi + c0 + q * 16, hi);
+    st_global_256(dst_lo + c0 + q * 16, lo);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sW = base, sA = base + kOffA2, sBar = base + kOffBar2;
+  // barriers: full[5] @0 (used in CTA 0), empty[5] @40, wfull @80, tfull[2] @88, tempty[2] @104 (CTA 0), tmem slot @120
+  const uint32_t bFull = sBar, bEmpty = sBar + 40, bW = sBar + 80, bTFull = sBar + 88, bTEmpty = sBar + 104;
+  const uint32_t sTmemSlot = sBar + 120;
+  float* bias_s = reinterpret_cast<float*>(gbase + kOffBias2);
+  const uint32_t rank = cluster_rank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots2; ++i) {
+      mbar_init(bFull + 8 * i, 1);          // CTA 0: one arrive.expect_tx for both CTAs' boxes
+      mbar_init(bEmpty + 8 * i, 1);         // multicast commit from CTA 0
+    }
+    mbar_init(bW, 1);
+    mbar_init(bTFull, 1); mbar_init(bTFull + 8, 1);
+    mbar_init(bTEmpty, 8); mbar_init(bTEmpty + 8, 8);   // 4 epilogue warps x 2 CTAs arrive on CTA 0's barrier
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(kTmemCols2) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();                          // barriers initialised, TMEM slot written
+  if (warp == 0) {
+    if (elect_one()) {
+      // this CTA's half of the weight image
+      mbar_expect_tx(bW, kWHalf);
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)rank * kWHalf;
+      for (int i = 0; i < 9; ++i) bulk_load(sW + i * 8192u, src + (size_t)i * 8192u, 8192u, bW);
+    }
+    __syncwarp();
+    mbar_wait(bW, 0);                       // own half landed ...
+  }
+  __syncthreads();
+  cluster_sync_all();                       // ... and the peer's too; all barriers of both CTAs are initialised
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar2 + 120);
+
+  const int per_img = a.tiles_x * a.tiles_y;
+  const int npairs = (a.ntiles + 1) >> 1;
+  const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs; boxes signal CTA 0's full barrier)
+    uint32_t j = 0;
+    for (int pair = cid; pair < npairs; pair += nclusters) {
+      int tile = 2 * pair + (int)rank;
+      if (tile >= a.ntiles) tile = a.ntiles - 1;            // odd tail: load a valid tile, its result is not stored
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y0 = (rem / a.tiles_x) * kTileRows, x0 = (rem % a.tiles_x) * kTileCols;
+#pragma unroll
+      for (int p = 0; p < 2; ++p, ++j) {
+        const uint32_t slot = j % kSlots2, use = j / kSlots2;
+        mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
+        if (elect_one()) {
+          if (rank == 0) mbar_expect_tx(bFull + 8 * slot, 2 * kPlaneBytes);
+          tma_load_4d_2sm(sA + slot * kPlaneSlot, &tmap, map_to_cta(bFull + 8 * slot, 0), 0, x0 - 1, y0 - 1, img * 2 + p);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (CTA 0 only)
+    if (rank == 0) {
+      const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
+      uint32_t j = 0;
+      int it = 0;
+      for (int pair = cid; pair < npairs; pair += nclusters, ++it) {
+        const uint32_t acc = it & 1;
+        mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+        const uint32_t d_tmem = tmem_base + acc * kAccCols2;
+#pragma unroll
+        for (int p = 0; p < 2; ++p, ++j) {
+          const uint32_t slot = j % kSlots2, use = j / kSlots2;
+          mbar_wait(bFull + 8 * slot, use & 1);
+          tc_fence_after();
+          const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (elect_one()) {
+            if (p == 0) issue_plane2<true>(d_tmem, a_lo, w_lo);
+            else issue_plane2<false>(d_tmem, a_lo, w_lo);
+            umma_commit_2sm(bEmpty + 8 * slot);
+            if (p == 1) umma_commit_2sm(bTFull + 8 * acc);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (each CTA drains its own 128 TMEM lanes)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    const size_t hw = (size_t)a.H * a.W;
+    const uint32_t tempty0 = map_to_cta(bTEmpty, 0);
+    int it = 0;
+    for (int pair = cid; pair < npairs; pair += nclusters, ++it) {
+      const int tile = 2 * pair + (int)rank;
+      const bool live = tile < a.ntiles;
+      const int tl = live ? tile : a.ntiles - 1;
+      const int img = tl / per_img, rem = tl - img * per_img;
+      const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
+      const uint32_t acc = it & 1;
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols2;
+      const bool st = live && y < a.H && x < a.W;
+      const size_t pix = (size_t)y * a.W + x;
+      __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+      __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
+      {
+        uint32_t r0[32], r1[32], r2[32];
+        tmem_ld32(taddr + 0, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + 128, r2);
+        tmem_ld_wait();
+        if (st) store_32ch(o_hi, o_lo, r0, r1, r2, bias_s, 0, a.slope);
+      }
+      {
+        uint32_t r0[32], r1[32], r2[32];
+        tmem_ld32(taddr + 64, r0);
+        tmem_ld32(taddr + 96, r1);
+        tmem_ld32(taddr + 160, r2);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);
+        if (st) store_32ch(o_hi, o_lo, r0, r1, r2, bias_s, 32, a.slope);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                       // the peer may still be reading TMEM / signalling our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols2) : "memory");
+  }
+}
+}  // namespace two
+
+// ---------------------------------------------------------------------------------------------
 // Probes (test hooks): establish, on hardware, how a tcgen05 shared-memory descriptor addresses
 // memory, and what a TMA box load leaves in shared memory.
 // ---------------------------------------------------------------------------------------------
@@ -510,6 +757,8 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<64>::kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<16>::kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(two::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)two::kSmemBytes2);
     if (e != cudaSuccess) {
       set_error(std::string("cudaFuncSetAttribute(conv_tc_kernel): ") + cudaGetErrorString(e));
       rc = 1;
@@ -545,6 +794,20 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   fill_common(a, plan, nimg, variant);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
   conv_tc_kernel<64><<<grid, kThreads, Geo<64>::kSmemBytes, st>>>(plan->map[in_buf], a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st) {
+  TcArgs a{};
+  a.w_img = L.w_mid_tc2;
+  a.bias = L.bias;
+  a.out = plan->act[in_buf ^ 1];
+  a.slope = slope;
+  a.C = 64;
+  fill_common(a, plan, nimg, 0);
+  const int npairs = (a.ntiles + 1) / 2;
+  const int nclusters = npairs < plan->num_sms / 2 ? npairs : plan->num_sms / 2;
+  two::conv_tc2_kernel<<<2 * nclusters, kThreads, two::kSmemBytes2, st>>>(plan->map[in_buf], a);
   return cudaGetLastError();
 }
 

@@ -84,6 +84,7 @@ struct DncnnLayerW {
   const float* bias_host;     // HOST [64] bias of the first layer
   const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
   const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][2 (hi,lo)][64 oc][64 ci] fp16, 128B-swizzled rows
+  const __half* w_mid_tc2; // 2-CTA engine: [cta 2][tap 9][w_hi half 32 rows | w_lo half 32 rows][64 ci] fp16, swizzled
   const float* w_last;    // [Cout][9][64 ci]                            last layer (SIMT engine)
   const __half* w_last_tc; // [9 taps][2][16 rows][64 ci] fp16 swizzled, rows >= Cout zero   last layer (tcgen05 engine)
   const float* bias;      // [Cout of this layer]
@@ -101,6 +102,7 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 void tc_plan_destroy(TcPlan* p);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
+cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
                                 float residual_sign, int clamp, float* out, int variant, cudaStream_t st);
 int tc_num_sms();

@@ -162,7 +162,9 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
-      if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+      if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && !(h->tc_variant & 16)) {
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
+      } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
       } else {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_simt(nimg, d.H, d.W, h->act[src], h->layers[l], h->slope, h->act[src ^ 1], st));
@@ -636,6 +638,25 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dh, img.size()));
       PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
       L.w_mid_tc = dh;
+      // 2-CTA engine: CTA r keeps, per tap, w_hi[32r:32r+32] followed by w_lo[32r:32r+32] (64 rows of 128 B, swizzled by local row)
+      std::vector<__half> img2((size_t)2 * 9 * 64 * 64);
+      for (int r = 0; r < 2; ++r)
+        for (int tp = 0; tp < 9; ++tp)
+          for (int lr = 0; lr < 64; ++lr) {
+            const int o = 32 * r + (lr & 31);
+            const bool is_lo = lr >= 32;
+            for (int c = 0; c < 64; ++c) {
+              const float v = w[((size_t)o * 64 + c) * 9 + tp];
+              const __half hi = __float2half_rn(v);
+              const __half val = is_lo ? __float2half_rn(v - __half2float(hi)) : hi;
+              const int chunk = (c >> 3) ^ (lr & 7);
+              img2[(((size_t)r * 9 + tp) * 64 + lr) * 64 + chunk * 8 + (c & 7)] = val;
+            }
+          }
+      __half* dh2 = nullptr;
+      PDS_TRY(dev_alloc(h, &dh2, img2.size()));
+      PDS_CUDA_OK(cudaMemcpy(dh2, img2.data(), img2.size() * sizeof(__half), cudaMemcpyHostToDevice));
+      L.w_mid_tc2 = dh2;
     }
   }
   // activation buffers
