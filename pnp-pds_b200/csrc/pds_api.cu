@@ -162,7 +162,11 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
-      if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && !(h->tc_variant & 16)) {
+      // body layers: the 2-CTA (cta_group::2) kernel for large launches, the 1-CTA kernel when there are too few
+      // tiles to fill CTA pairs evenly (single small images); PDS_TC_VARIANT bit 4 / bit 5 force 1-CTA / 2-CTA
+      const long long ntiles = (long long)nimg * ((d.H + 15) / 16) * ((d.W + 7) / 8);
+      const bool two_cta = (h->tc_variant & 32) || (!(h->tc_variant & 16) && ntiles >= 4096);
+      if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));

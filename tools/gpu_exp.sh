@@ -1,7 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-for v in 0 2 4 6 8 14; do
+for v in 0 2 6 8 14 16 22; do
   PDS_TC_VARIANT=$v timeout 600 python bench.py --steps 3 --warmup 3 --workload cfg4 --batch 16 --no-cpu-baseline > gpurun_out/exp_v$v.json 2> gpurun_out/exp_v$v.err
   python - $v <<'PY'
 import json,sys
