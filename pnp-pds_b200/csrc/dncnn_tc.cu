@@ -171,6 +171,11 @@ __device__ __forceinline__ void store_half_row(__half* dst_hi, __half* dst_lo, c
   }
 }
 
+// Programmatic dependent launch: a layer's CTAs may start (barrier init, TMEM alloc, weight loads) while the
+// previous layer's grid is still draining; everything that touches the previous layer's output waits here.
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t elect_one() {
   uint32_t pred;
   asm volatile(
@@ -245,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + G::kOffBar + 136);
+  pdl_launch_dependents();
 
   const int per_img = a.tiles_x * a.tiles_y;
   if (warp == 0) {
@@ -255,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         bulk_load(sW + i * G::kWTile, reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)i * G::kWTile, G::kWTile, bW);
     }
     __syncwarp();
+    pdl_wait_prior_grid();                                  // activations of the previous layer are complete and visible
     uint32_t j = 0;     // plane sequence number: 2*it + p
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
       const int img = tile / per_img, rem = tile - img * per_img;
@@ -509,12 +516,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();                       // ... and the peer's too; all barriers of both CTAs are initialised
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar2 + 120);
+  pdl_launch_dependents();
 
   const int per_img = a.tiles_x * a.tiles_y;
   const int npairs = (a.ntiles + 1) >> 1;
   const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs; boxes signal CTA 0's full barrier)
+    pdl_wait_prior_grid();
     uint32_t j = 0;
     for (int pair = cid; pair < npairs; pair += nclusters) {
       int tile = 2 * pair + (int)rank;
@@ -774,6 +783,21 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 static void fill_common(TcArgs& a, TcPlan* plan, int nimg, int variant) {
   a.H = plan->H;
   a.W = plan->W;
@@ -793,8 +817,7 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   a.C = 64;
   fill_common(a, plan, nimg, variant);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  conv_tc_kernel<64><<<grid, kThreads, Geo<64>::kSmemBytes, st>>>(plan->map[in_buf], a);
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_kernel<64>, grid, kThreads, Geo<64>::kSmemBytes, st, plan->map[in_buf], a);
 }
 
 cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st) {
@@ -807,8 +830,7 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
   fill_common(a, plan, nimg, 0);
   const int npairs = (a.ntiles + 1) / 2;
   const int nclusters = npairs < plan->num_sms / 2 ? npairs : plan->num_sms / 2;
-  two::conv_tc2_kernel<<<2 * nclusters, kThreads, two::kSmemBytes2, st>>>(plan->map[in_buf], a);
-  return cudaGetLastError();
+  return launch_pdl(two::conv_tc2_kernel, 2 * nclusters, kThreads, two::kSmemBytes2, st, plan->map[in_buf], a);
 }
 
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in, float residual_sign,
@@ -823,8 +845,7 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
   a.clamp = clamp;
   fill_common(a, plan, nimg, variant & 4);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  conv_tc_kernel<16><<<grid, kThreads, Geo<16>::kSmemBytes, st>>>(plan->map[in_buf], a);
-  return cudaGetLastError();
+  return launch_pdl(conv_tc_kernel<16>, grid, kThreads, Geo<16>::kSmemBytes, st, plan->map[in_buf], a);
 }
 
 }  // namespace pds

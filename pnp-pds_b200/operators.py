@@ -24,6 +24,8 @@ def load_blur_kernel(path_kernel):
     if isinstance(path_kernel, np.ndarray):
         return np.asarray(path_kernel, dtype=np.float64)
     p = str(path_kernel)
+    if not os.path.exists(p) and os.path.exists(os.path.splitext(p)[0] + ".npy"):
+        p = os.path.splitext(p)[0] + ".npy"          # converted kernel next to a missing .mat
     if p.endswith(".npy"):
         return np.load(p).astype(np.float64)
     if p.endswith(".npz"):
