@@ -79,11 +79,14 @@ typedef struct {
 } pds_item_params_t;
 
 /* Number of double-precision partial sums recorded per item per iteration. */
-#define PDS_TRACE_WIDTH 4
+#define PDS_TRACE_WIDTH 5
 /* trace[it][b][0] = ||t||^2  with y = sigma t the dual variable before the l2-ball scaling (methods A, B)
  * trace[it][b][1] = ||x_{k+1} - x_k||^2      numerator of c[i]      (iteration.py:187)
  * trace[it][b][2] = ||x_k||^2                denominator of c[i]
- * trace[it][b][3] = ||x_{k+1} - x_true||^2   n * mse of eval_psnr   (utils_eval.py:4-7) */
+ * trace[it][b][3] = ||x_{k+1} - x_true||^2   n * mse of eval_psnr   (utils_eval.py:4-7)
+ * trace[it][b][4] = sum of the SSIM map over all window positions (eval_ssim, utils_eval.py:9-12) on the
+ *                   iterations selected by pds_set_ssim, 0 elsewhere; mean SSIM = value / positions with
+ *                   positions = C (H-6)(W-6) for colour, H (W-6) for gray (channel_axis=0 quirk) */
 
 const char* pds_last_error(void);
 int pds_abi_version(void);
@@ -101,6 +104,9 @@ int pds_set_blur_kernel(pds_handle_t h, const double* kernel_host, int l);
 int pds_set_mask(pds_handle_t h, const uint8_t* mask_host);
 /* n == batch, or n == 1 to broadcast */
 int pds_set_item_params(pds_handle_t h, const pds_item_params_t* params_host, int n);
+/* per-iteration SSIM on the device: 0 = off, 1 = every iteration (as the reference, iteration.py:189),
+ * 2 = only the last iteration of each pds_run / pds_restore_host call.  Needs x_true. */
+int pds_set_ssim(pds_handle_t h, int mode);
 /* inner trip counts and step size of the ADMM cross-check loops: m1, m2, gammaInADMMStep1 (iteration.py:10) */
 int pds_set_admm(pds_handle_t h, int m1, int m2, float gamma_step1);
 /* PDSW weight blob (models/weights.py) — replaces Denoiser.__init__/load_network (denoiser.py:9-32) */

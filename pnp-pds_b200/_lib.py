@@ -15,7 +15,7 @@ _lib = None
 METHODS = {"A": 0, "B": 1, "C": 2, "FBS": 3, "RED": 4, "ADMM_B2": 5, "ADMM_C": 6, "RED_C": 7}
 DEG_OPS = {"Id": 0, "blur": 1, "random_sampling": 2}
 CONV_ENGINES = {"tcgen05": 0, "simt": 1}
-TRACE_WIDTH = 4
+TRACE_WIDTH = 5
 PROF_CATS = ("primal", "dual", "l1ball", "conv_first", "conv_mid", "conv_last")
 
 
@@ -44,6 +44,7 @@ def _declare(lib):
         "pds_set_mask": (i, [vp, C.POINTER(C.c_uint8)]),
         "pds_set_item_params": (i, [vp, C.POINTER(PdsItemParams), i]),
         "pds_set_admm": (i, [vp, i, i, f]),
+        "pds_set_ssim": (i, [vp, i]),
         "pds_load_dncnn": (i, [vp, vp, sz]),
         "pds_phi": (i, [vp, vp, vp, vp]),
         "pds_phi_adj": (i, [vp, vp, vp, vp]),

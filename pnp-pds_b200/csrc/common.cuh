@@ -35,7 +35,7 @@ struct ItemParams {
   float g1, g2, eps, eta, lam, alpha;
 };
 
-enum : int { SUM_T2 = 0, SUM_DX2 = 1, SUM_X2 = 2, SUM_ERR2 = 3, NSUM = PDS_TRACE_WIDTH };
+enum : int { SUM_T2 = 0, SUM_DX2 = 1, SUM_X2 = 2, SUM_ERR2 = 3, SUM_SSIM = 4, NSUM = PDS_TRACE_WIDTH, NACC = 4 };  // NACC: sums the dual kernels produce
 
 constexpr int kMid = 64;  // channel width of the DnCNN body (simple_CNN n_ch, basic_models.py:9)
 

@@ -71,6 +71,9 @@ cudaError_t launch_blur_apply(const Dims& d, const BlurTaps& taps, int adjoint, 
 cudaError_t launch_primal_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);
 cudaError_t launch_dual_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);
 
+// ---- pds_ssim.cu ---------------------------------------------------------------
+cudaError_t launch_ssim(const Dims& d, const float* xtrue, const float* x, unsigned* mm, double* sums_cur, cudaStream_t st);
+
 // ---- pds_l1ball.cu ----------------------------------------------------------
 // s_out = P_{l1-ball(eta)}(z), z = s_in - gamma1*sigma*t (t != null) or z = s_in.
 // eta per item from prm (eta_override < 0) or the scalar eta_override.

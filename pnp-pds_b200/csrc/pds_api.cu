@@ -45,6 +45,9 @@ struct pds_handle_s {
   bool have_params = false;
   double* sums = nullptr;      // [max_iter][B][NSUM]
   double* scratch = nullptr;   // [B]
+  unsigned* mm = nullptr;      // [B][2] min/max keys for the SSIM data range
+  int ssim_mode = 0;           // 0 off, 1 every iteration, 2 last iteration of each run
+  bool ssim_now = false;
   // blur
   BlurTaps taps{};
   bool have_blur = false;
@@ -184,6 +187,16 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
   return 0;
 }
 
+// eval_ssim(x_true, x_{k+1}) of iteration.py:189 when requested for this iteration
+int post_iteration(pds_handle_s* h, const float* x_new, cudaStream_t st) {
+  if (h->ssim_now && h->have_true) {
+    const size_t row = (size_t)h->d.B * NSUM;
+    PDS_CUDA_OK(launch_ssim(h->d, h->xtrue, x_new, h->mm, h->sums + (size_t)h->iter * row, st));
+    h->launches += 2;
+  }
+  return 0;
+}
+
 StepArgs step_args(pds_handle_s* h) {
   StepArgs a{};
   a.d = h->d;
@@ -218,6 +231,7 @@ int pds_iteration(pds_handle_s* h, cudaStream_t st) {
   // y_{k+1}
   if (blur) PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_blur(a, h->taps, st));
   else PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_pointwise(a, st));
+  PDS_TRY(post_iteration(h, a.xn, st));
   h->cur ^= 1;
   if (h->cfg.method == PDS_METHOD_B) h->scur ^= 1;
   h->iter++;
@@ -270,6 +284,7 @@ int fbs_red_iteration(pds_handle_s* h, cudaStream_t st) {
   }
   const size_t row = (size_t)d.B * NSUM;
   PDS_LAUNCH(h, launch_metrics(d, xn, x, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  PDS_TRY(post_iteration(h, xn, st));
   h->cur ^= 1;
   h->iter++;
   return 0;
@@ -359,6 +374,7 @@ int admm_b2_iteration(pds_handle_s* h, cudaStream_t st) {
   PDS_TRY(lin(h, CB_Y, 4, y, y, w0, sn, z, nullptr, st));
   const size_t row = (size_t)h->d.B * NSUM;
   PDS_LAUNCH(h, launch_metrics(h->d, x, x_prev, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  PDS_TRY(post_iteration(h, x, st));
   h->cur ^= 1;
   h->scur ^= 1;
   h->iter++;
@@ -393,6 +409,7 @@ int admm_c_iteration(pds_handle_s* h, cudaStream_t st) {
   PDS_TRY(lin(h, CC_D, 3, dd, dd, x, z, nullptr, nullptr, st));
   const size_t row = (size_t)h->d.B * NSUM;
   PDS_LAUNCH(h, launch_metrics(h->d, x, x_prev, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  PDS_TRY(post_iteration(h, x, st));
   h->cur ^= 1;
   h->iter++;
   return 0;
@@ -464,6 +481,7 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   A(&h->prm, (size_t)cfg->batch);
   A(&h->sums, (size_t)cfg->max_iter * cfg->batch * NSUM);
   A(&h->scratch, (size_t)cfg->batch);
+  A(&h->mm, (size_t)cfg->batch * 2);
   if (rc) { pds_destroy(h); return rc; }
   *out = h;
   return 0;
@@ -745,6 +763,7 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
   PDS_REQUIRE(n_iter >= 0 && h->iter + n_iter <= h->cfg.max_iter, "n_iter exceeds the max_iter the handle was created with");
   cudaStream_t st = (cudaStream_t)stream;
   for (int i = 0; i < n_iter; ++i) {
+    h->ssim_now = h->ssim_mode == 1 || (h->ssim_mode == 2 && i == n_iter - 1);
     if (h->cfg.method <= PDS_METHOD_C) PDS_TRY(pds_iteration(h, st));
     else if (h->cfg.method <= PDS_METHOD_RED) PDS_TRY(fbs_red_iteration(h, st));
     else {
@@ -753,6 +772,13 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
       else PDS_TRY(admm_c_iteration(h, st));
     }
   }
+  return 0;
+}
+
+int pds_set_ssim(pds_handle_t h, int mode) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(mode >= 0 && mode <= 2, "ssim mode must be 0 (off), 1 (every iteration) or 2 (last iteration of each run)");
+  h->ssim_mode = mode;
   return 0;
 }
 

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(BlurArgs a) {
   float* tile = smem;
   float* tw = smem + hrows * pitch;
   int* toff = reinterpret_cast<int*>(tw + a.ntaps);
-  __shared__ double red[NSUM * (kThreads / 32)];
+  __shared__ double red[NACC * (kThreads / 32)];
 
   const int plane = blockIdx.y;            // b*C + c
   const int b = plane / d.C;
@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(BlurArgs a) {
     }
   }
   if constexpr (MODE == kDual) {
-    double v[NSUM] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
-    block_accumulate<NSUM>(v, a.s.sums_cur + (size_t)b * NSUM, red);
+    double v[NACC] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
+    block_accumulate<NACC>(v, a.s.sums_cur + (size_t)b * NSUM, red);
   }
 }
 
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                       // [HR][PITCH]
   float* wbox = smem + HR * PITCH;          // [2RY+1][WROW]
-  __shared__ double red[NSUM * 8];
+  __shared__ double red[NACC * 8];
   const Dims d = a.s.d;
   const int plane = blockIdx.y;
   const int b = plane / d.C;
@@ -286,8 +286,8 @@ __global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
     }
   }
   if constexpr (MODE == kDual) {
-    double v[NSUM] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
-    block_accumulate<NSUM>(v, a.s.sums_cur + (size_t)b * NSUM, red);
+    double v[NACC] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
+    block_accumulate<NACC>(v, a.s.sums_cur + (size_t)b * NSUM, red);
   }
 }
 

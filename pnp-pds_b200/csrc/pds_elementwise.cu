@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kThreads) primal_pw_kernel(StepArgs a) {
 // w = sigma t + g2 (Phi(2 x+ - x) [+ 2 s+ - s]);  A,B: t+ = w - g2 b ;  C: y+ = gkl(w)
 template <int V, bool MASK, int METHOD>
 __global__ void __launch_bounds__(kThreads) dual_pw_kernel(StepArgs a) {
-  __shared__ double red[NSUM * (kThreads / 32)];
+  __shared__ double red[NACC * (kThreads / 32)];
   const int b = blockIdx.y;
   const ItemParams p = a.prm[b];
   const float sg = item_sigma(METHOD, a.sums_prev, b, p);
@@ -135,8 +135,8 @@ __global__ void __launch_bounds__(kThreads) dual_pw_kernel(StepArgs a) {
     }
     store<V>(a.t, o, tn);
   }
-  double v[NSUM] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
-  block_accumulate<NSUM>(v, a.sums_cur + (size_t)b * NSUM, red);
+  double v[NACC] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
+  block_accumulate<NACC>(v, a.sums_cur + (size_t)b * NSUM, red);
 }
 
 template <int V>
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) prox_gkl_kernel(Dims d, const float*
 template <int V>
 __global__ void __launch_bounds__(kThreads) metrics_kernel(Dims d, const float* __restrict__ xn, const float* __restrict__ x,
                                                            const float* __restrict__ xtrue, double* __restrict__ sums_cur) {
-  __shared__ double red[NSUM * (kThreads / 32)];
+  __shared__ double red[NACC * (kThreads / 32)];
   const size_t base = (size_t)blockIdx.y * d.n;
   const int nv = d.n / V;
   float acc_dx = 0.f, acc_x = 0.f, acc_e = 0.f;
@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(kThreads) metrics_kernel(Dims d, const float* 
       }
     }
   }
-  double v[NSUM] = {0.0, (double)acc_dx, (double)acc_x, (double)acc_e};
-  block_accumulate<NSUM>(v, sums_cur + (size_t)blockIdx.y * NSUM, red);
+  double v[NACC] = {0.0, (double)acc_dx, (double)acc_x, (double)acc_e};
+  block_accumulate<NACC>(v, sums_cur + (size_t)blockIdx.y * NSUM, red);
 }
 
 __global__ void __launch_bounds__(kThreads) axpbypcz_kernel(size_t n, float a, const float* __restrict__ p, float b,

@@ -124,6 +124,11 @@ class Engine:
                                    float(p.get("eta", 0.0)), float(p.get("lam", 1.0)), float(p.get("alpha", 1.0)))
         _lib.check(self.lib.pds_set_item_params(self._h, arr, len(params)))
 
+    def set_ssim(self, mode: str | int):
+        """'none' | 'all' (every iteration, as the reference) | 'final' (last iteration of each run)."""
+        mode = {"none": 0, "all": 1, "final": 2}.get(mode, mode)
+        _lib.check(self.lib.pds_set_ssim(self._h, int(mode)))
+
     def set_admm(self, m1: int, m2: int, gamma_step1: float):
         """m1, m2, gammaInADMMStep1 of iteration.test_iter (inner trip counts / step of algorithm/admm.py)."""
         _lib.check(self.lib.pds_set_admm(self._h, int(m1), int(m2), float(gamma_step1)))
@@ -251,3 +256,12 @@ def metrics_from_traces(tr: np.ndarray, n: int):
         c = np.sqrt(tr[..., 1]) / np.sqrt(tr[..., 2])
         psnr = 10.0 * np.log10(1.0 / (tr[..., 3] / n))
     return c, psnr
+
+
+def ssim_from_traces(tr: np.ndarray, C: int, H: int, W: int):
+    """Mean SSIM (utils_eval.py:9-12) per iteration and item; NaN where it was not evaluated."""
+    positions = (C * (H - 6) * (W - 6)) if C != 1 else (H * (W - 6))
+    raw = tr[..., 4]
+    if positions <= 0:
+        return np.full(raw.shape, np.nan)
+    return np.where(raw != 0.0, raw / positions, np.nan)

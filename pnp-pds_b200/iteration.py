@@ -11,7 +11,8 @@ from typing import Sequence
 
 import numpy as np
 
-from .engine import RESIDENT_METHODS, Engine, canonical_method, l1_ball_radius, l2_ball_radius, metrics_from_traces
+from .engine import (RESIDENT_METHODS, Engine, canonical_method, l1_ball_radius, l2_ball_radius, metrics_from_traces,
+                     ssim_from_traces)
 from .models.weights import DnCNNWeights, load_weights
 from .operators import ObservationOperator, sampling_mask
 from .utils.utils_eval import eval_ssim
@@ -88,6 +89,7 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         if mid in ("ADMM_B2", "ADMM_C", "RED_C"):
             eng.set_admm(m1, m2, gammaInADMMStep1)
         eng.load_dncnn(weights)
+        eng.set_ssim(ssim if x_true is not None else "none")
         import torch
         t0 = time.perf_counter()
         x, s, tr = eng.restore_host(x_0, x_obsrv, x_true, int(max_iter), want_s=True)
@@ -99,11 +101,7 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
     c, psnr = metrics_from_traces(tr, n)                              # [it, B]
     x = x.reshape(x_0.shape)
     s = s.reshape(x_0.shape)
-    ssim_data = np.full((int(max_iter), B), np.nan)
-    if ssim != "none" and x_true is not None and max_iter > 0:
-        xt = np.asarray(x_true)
-        for b in range(B):
-            ssim_data[-1, b] = eval_ssim(xt[b], x[b])
+    ssim_data = ssim_from_traces(tr, C, H, W)                          # [it, B]; evaluated on the device
     return dict(x=x, s=s, c=c, psnr=psnr, ssim=ssim_data, time_per_iter=wall / max(1, int(max_iter)), traces=tr,
                 launches=launches)
 
@@ -114,8 +112,8 @@ def test_iter(x_0, x_obsrv, x_true, phi, adj_phi, gamma1, gamma2, alpha_s, alpha
     reference (iteration.py:10,196): (x_n, s_n + 0.5, c, psnr_data, ssim_data, average_time).
 
     Differences, by design: x_n is float32 (as the reference's denoiser output is); ssim_data holds
-    the final SSIM in its last entry and NaN before it (per-iteration SSIM would force a device->host
-    copy every iteration; pass through run_batch(ssim=...) to change); average_time is wall seconds
+    the final SSIM in its last entry and NaN before it (run_batch(ssim="all") evaluates it on the device
+    every iteration like the reference, at a few percent of the iteration time); average_time is wall seconds
     per iteration including the H2D/D2H copies, not process CPU seconds; an unknown method raises
     ValueError instead of printing and crashing on an unbound variable (iteration.py:183-185)."""
     p = dict(gamma1=gamma1, gamma2=gamma2, alpha_s=alpha_s, alpha_n=alpha_n, myLambda=myLambda, gaussian_nl=gaussian_nl,

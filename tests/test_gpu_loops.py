@@ -102,6 +102,33 @@ def test_test_iter_signature_and_errors(g_loops, assets):
         iteration.test_iter(*args[:3], lambda z: z, lambda z: z, *args[5:], "A-Proposed", 1, 1.0)
 
 
+@pytest.mark.parametrize("tag", ["A_blur_g", "A_blur_c", "B_rs_c"])
+def test_ssim_trace_on_device(g_loops, assets, tag):
+    """ssim="all": eval_ssim(x_true, x_{k+1}) every iteration on the device (gray: 1-D windows per row, colour: 7x7)
+    against the oracle's restatement of scikit-image's defaults evaluated on the device iterate (parity unpinned)."""
+    from pnp_pds_b200 import iteration, operators
+    case = json.loads(str(g_loops[f"{tag}/case"]))
+    arch = "DnCNN_nobn_nch_1_nlev_0.01" if case["ch"] == 1 else "DnCNN_nobn_nch_3_nlev_0.01"
+    phi, adj = operators.get_observation_operators(case["deg_op"], assets["blur_1"], case.get("r", 1.0))
+    prm = dict(gamma1=case["gamma1"], gamma2=case["gamma2"], alpha_s=case["alpha_s"], alpha_n=case["alpha_n"], myLambda=1.0,
+               gaussian_nl=case["gaussian_nl"], sp_nl=case["sp_nl"], poisson_alpha=300, r=case.get("r", 1.0))
+    xt = g_loops[f"{tag}/x_true"]
+    vals = []
+    for n in (1, 2, 3):
+        res = iteration.run_batch(g_loops[f"{tag}/x0"][None], g_loops[f"{tag}/obs"][None], xt[None], phi, adj, prm, weights_path(arch), n,
+                                  case["method"], case["ch"], ssim="all")
+        assert res["ssim"].shape == (n, 1) and np.all(np.isfinite(res["ssim"]))
+        assert abs(res["ssim"][-1, 0] - O.eval_ssim(xt, res["x"][0])) < 2e-6
+        vals.append(res["ssim"][:, 0])
+    assert np.allclose(vals[2][:2], vals[1], atol=1e-12) and np.allclose(vals[1][:1], vals[0], atol=1e-12)
+    res = iteration.run_batch(g_loops[f"{tag}/x0"][None], g_loops[f"{tag}/obs"][None], xt[None], phi, adj, prm, weights_path(arch), 3,
+                              case["method"], case["ch"], ssim="final")
+    assert np.all(np.isnan(res["ssim"][:-1, 0])) and abs(res["ssim"][-1, 0] - vals[2][-1]) < 1e-12
+    res = iteration.run_batch(g_loops[f"{tag}/x0"][None], g_loops[f"{tag}/obs"][None], xt[None], phi, adj, prm, weights_path(arch), 2,
+                              case["method"], case["ch"], ssim="none")
+    assert np.all(np.isnan(res["ssim"]))
+
+
 def test_batched_mixed_parameters_match_single_runs(g_loops, assets):
     """A batch that mixes grid points (per-item gamma / alpha) reproduces the individual restorations."""
     from pnp_pds_b200 import iteration, operators

@@ -138,12 +138,18 @@ def test_item_params_quirks():
 
 def test_metrics_from_traces():
     from pnp_pds_b200.engine import metrics_from_traces
-    tr = np.zeros((2, 1, 4))
+    tr = np.zeros((2, 1, 5))
     tr[:, 0, 1] = [4.0, 1.0]
     tr[:, 0, 2] = [16.0, 16.0]
     tr[:, 0, 3] = [0.01 * 100, 0.0001 * 100]
     c, psnr = metrics_from_traces(tr, 100)
     assert np.allclose(c[:, 0], [0.5, 0.25]) and np.allclose(psnr[:, 0], [20.0, 40.0])
+    from pnp_pds_b200.engine import ssim_from_traces
+    tr[1, 0, 4] = 0.5 * 3 * (20 - 6) * (10 - 6)
+    s3 = ssim_from_traces(tr, 3, 20, 10)
+    assert np.isnan(s3[0, 0]) and abs(s3[1, 0] - 0.5) < 1e-15
+    tr[1, 0, 4] = 0.25 * 20 * (10 - 6)
+    assert abs(ssim_from_traces(tr, 1, 20, 10)[1, 0] - 0.25) < 1e-15      # gray: H rows x (W-6) one-dimensional windows
 
 
 def test_ssim_restatement_matches_oracle_and_basic_properties():
