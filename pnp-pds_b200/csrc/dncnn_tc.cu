@@ -372,6 +372,214 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------
+// First layer (Cin = 1|3 -> 64) on the tensor pipe.  K = 9*Cin <= 27 is padded to 32 (two k-steps); the
+// A operand is an explicit im2col tile that four producer warps build in shared memory: thread m owns
+// pixel m of the 16x8 tile, reads its 3x3xCin window (zero padding, input clamp of denoiser.py:40), splits
+// to fp16 hi/lo and writes the 64 meaningful bytes of its 128-byte row in SWIZZLE_128B order.  MMAs and the
+// epilogue are those of the body layers (N=128 [w_hi;w_lo] for the hi plane, N=64 for the lo plane), so the
+// kernel is bound by writing the 256 B/pixel of activations, not by CUDA-core FMAs.
+// ---------------------------------------------------------------------------------------------
+namespace first {
+constexpr int kStages = 4, kThreadsF = 320;                 // 4 producer warps, 1 MMA warp, 4 epilogue warps, 1 spare
+constexpr uint32_t kWBytesF = 128 * 128;                    // [w_hi 64 rows ; w_lo 64 rows] x 128 B
+constexpr uint32_t kATile = 128 * 128;                      // one plane of one stage
+constexpr uint32_t kOffAF = kWBytesF, kOffBarF = kOffAF + kStages * 2 * kATile;
+constexpr uint32_t kOffBiasF = kOffBarF + 192, kOffStgF = kOffBiasF + 256;
+constexpr uint32_t kSmemBytesF = kOffStgF + 2 * 18 * 10 * 3 * 4 + 1024;       // + double-buffered input window (Cin <= 3)
+constexpr uint32_t kIdescN64 = kIdescBase | ((64u >> 3) << 17), kIdescN128 = kIdescBase | ((128u >> 3) << 17);
+
+struct FirstArgs {
+  const float* in;        // (nimg, CIN, H, W)
+  const __half* w_img;    // swizzled [128][64] fp16 image
+  const float* bias;
+  __half* out;
+  float slope;
+  int clamp_in;
+  int H, W, nimg, tiles_x, tiles_y, ntiles;
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sW = base, sA = base + kOffAF, sBar = base + kOffBarF;
+  // barriers: full[4] @0, empty[4] @32, wfull @64, tfull[2] @72, tempty[2] @88, tmem slot @104
+  const uint32_t bFull = sBar, bEmpty = sBar + 32, bW = sBar + 64, bTFull = sBar + 72, bTEmpty = sBar + 88, sTmemSlot = sBar + 104;
+  float* bias_s = reinterpret_cast<float*>(gbase + kOffBiasF);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bFull + 8 * i, 128);        // every producer thread arrives after its row is written
+      mbar_init(bEmpty + 8 * i, 1);
+    }
+    mbar_init(bW, 1);
+    mbar_init(bTFull, 1); mbar_init(bTFull + 8, 1);
+    mbar_init(bTEmpty, 4); mbar_init(bTEmpty + 8, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x >= 160 && threadIdx.x < 224) bias_s[threadIdx.x - 160] = a.bias[threadIdx.x - 160];
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // zero the A tiles once: chunks 4..7 of every row are never written again and never read by the two k-steps,
+  // but the padded part of chunk 3 (k = 27..31) must be zero
+  for (uint32_t i = threadIdx.x; i < kStages * 2 * kATile / 16; i += kThreadsF)
+    *reinterpret_cast<uint4*>(gbase + kOffAF + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarF + 104);
+  const int per_img = a.tiles_x * a.tiles_y;
+  const size_t hw = (size_t)a.H * a.W;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ im2col producers (thread m = pixel m of the tile)
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bW, kWBytesF);
+      bulk_load(sW, a.w_img, kWBytesF, bW);
+    }
+    const int m = threadIdx.x, ty = m >> 3, tx = m & 7;
+    // The (18 x 10 x Cin) input window of a tile is fetched cooperatively (each of the 128 producer threads loads
+    // PER elements, coalesced along x), kDepth tiles ahead of its use so DRAM latency is off the critical path,
+    // staged through a double-buffered shared-memory window, and then every thread gathers its own 3x3xCin patch.
+    constexpr int kWinPix = kHaloRows * kHaloPitch, kWin = kWinPix * CIN, PER = (kWin + 127) / 128, kDepth = 3;
+    float* stg = reinterpret_cast<float*>(gbase + kOffStgF);           // [2][kWin]
+    auto fetch = [&](int tile, float (&r)[PER]) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y0 = (rem / a.tiles_x) * kTileRows - 1, x0 = (rem % a.tiles_x) * kTileCols - 1;
+#pragma unroll
+      for (int j = 0; j < PER; ++j) {
+        const int idx = m + 128 * j;
+        float t = 0.f;
+        if (idx < kWin) {
+          const int c = idx / kWinPix, p = idx - c * kWinPix;
+          const int gy = y0 + p / kHaloPitch, gx = x0 + p % kHaloPitch;
+          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
+            t = __ldg(a.in + ((size_t)(img * CIN + c) * a.H + gy) * a.W + gx);
+            if (a.clamp_in) t = fminf(fmaxf(t, 0.f), 1.f);
+          }
+        }
+        r[j] = t;
+      }
+    };
+    float pre[kDepth][PER];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+      const int t0 = blockIdx.x + d * gridDim.x;
+      if (t0 < a.ntiles) fetch(t0, pre[d]);
+    }
+    int it = 0;
+    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += kDepth * gridDim.x) {
+#pragma unroll
+      for (int d = 0; d < kDepth; ++d, ++it) {
+        const int tile = tile0 + d * gridDim.x;
+        if (tile >= a.ntiles) break;
+        float* sw = stg + (it & 1) * kWin;
+#pragma unroll
+        for (int j = 0; j < PER; ++j)
+          if (m + 128 * j < kWin) sw[m + 128 * j] = pre[d][j];
+        if (tile + kDepth * (int)gridDim.x < a.ntiles) fetch(tile + kDepth * gridDim.x, pre[d]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");           // window of this tile complete (4 producer warps)
+        float v[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) v[(dy * 3 + dx) * CIN + ci] = sw[ci * kWinPix + (ty + dy) * kHaloPitch + tx + dx];
+      const uint32_t stage = it % kStages, use = it / kStages;
+      mbar_wait(bEmpty + 8 * stage, (use & 1) ^ 1);
+      const uint32_t row_hi = sA + stage * 2 * kATile + (uint32_t)m * 128u, row_lo = row_hi + kATile;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float v0 = v[8 * j + 2 * e], v1 = v[8 * j + 2 * e + 1];
+          const __half2 hh = __floats2half2_rn(v0, v1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+          hi[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          lo[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const uint32_t off = (uint32_t)((j ^ (m & 7)) * 16);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+      }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(bFull + 8 * stage);
+      }
+    }
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    mbar_wait(bW, 0);
+    const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1, stage = it % kStages, use = it / kStages;
+      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+      mbar_wait(bFull + 8 * stage, use & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 128u;
+      const uint32_t a_hi = (((sA + stage * 2 * kATile) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_lo = (((sA + stage * 2 * kATile + kATile) & 0x3FFFFu) >> 4) | (1u << 16);
+      if (elect_one()) {
+        umma_f16(d_tmem, desc64(a_hi, kHi), desc64(w_lo, kHi), kIdescN128, 0u);
+        umma_f16(d_tmem, desc64(a_hi + 2, kHi), desc64(w_lo + 2, kHi), kIdescN128, 1u);
+        umma_f16(d_tmem, desc64(a_lo, kHi), desc64(w_lo, kHi), kIdescN64, 1u);
+        umma_f16(d_tmem, desc64(a_lo + 2, kHi), desc64(w_lo + 2, kHi), kIdescN64, 1u);
+        umma_commit(bEmpty + 8 * stage);
+        umma_commit(bTFull + 8 * acc);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 9) {
+    // ------------------------------------------------------------ epilogue (same as the body layers)
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
+      const uint32_t acc = it & 1;
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 64, r2);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld32(taddr + 96, r3);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+      if (y < a.H && x < a.W) {
+        const size_t pix = (size_t)y * a.W + x;
+        __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+        __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
+        store_half_row(o_hi, o_lo, r0, r2, bias_s, 0, a.slope);
+        store_half_row(o_hi, o_lo, r1, r3, bias_s, 32, a.slope);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+}  // namespace first
+
+// ---------------------------------------------------------------------------------------------
 // 2-CTA variant of the body layer (cta_group::2): a cluster of two CTAs works on two pixel tiles at
 // once as ONE M=256 UMMA issued by CTA 0.  The B operand (weights) is split between the two CTAs'
 // shared memories, so every SM reads only half of B per MMA and keeps only half of the weight image
@@ -768,6 +976,10 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
       e = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<16>::kSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(two::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)two::kSmemBytes2);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(first::conv_first_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first::kSmemBytesF);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(first::conv_first_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first::kSmemBytesF);
     if (e != cudaSuccess) {
       set_error(std::string("cudaFuncSetAttribute(conv_tc_kernel): ") + cudaGetErrorString(e));
       rc = 1;
@@ -831,6 +1043,28 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
   const int npairs = (a.ntiles + 1) / 2;
   const int nclusters = npairs < plan->num_sms / 2 ? npairs : plan->num_sms / 2;
   return launch_pdl(two::conv_tc2_kernel, 2 * nclusters, kThreads, two::kSmemBytes2, st, plan->map[in_buf], a);
+}
+
+cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
+                                 cudaStream_t st) {
+  first::FirstArgs a{};
+  a.in = in;
+  a.w_img = L.w_first_tc;
+  a.bias = L.bias;
+  a.out = plan->act[0];
+  a.slope = slope;
+  a.clamp_in = clamp_in;
+  a.H = plan->H;
+  a.W = plan->W;
+  a.nimg = nimg;
+  a.tiles_x = (plan->W + kTileCols - 1) / kTileCols;
+  a.tiles_y = (plan->H + kTileRows - 1) / kTileRows;
+  a.ntiles = a.tiles_x * a.tiles_y * nimg;
+  const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
+  if (C == 1) first::conv_first_tc_kernel<1><<<grid, first::kThreadsF, first::kSmemBytesF, st>>>(a);
+  else if (C == 3) first::conv_first_tc_kernel<3><<<grid, first::kThreadsF, first::kSmemBytesF, st>>>(a);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
 }
 
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in, float residual_sign,

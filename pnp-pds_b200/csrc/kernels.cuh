@@ -85,6 +85,7 @@ cudaError_t launch_l1ball(const Dims& d, const float* s_in, const float* t, cons
 struct DncnnLayerW {
   const float* w_first_host;  // HOST [9*Cin][64] (k = tap*Cin + ci): handed to the first-layer kernel by value (constant bank)
   const float* bias_host;     // HOST [64] bias of the first layer
+  const __half* w_first_tc;   // tcgen05 first layer: [w_hi 64 rows ; w_lo 64 rows] x 128 B, k = tap*Cin+ci in the first 27 halves, swizzled
   const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
   const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][2 (hi,lo)][64 oc][64 ci] fp16, 128B-swizzled rows
   const __half* w_mid_tc2; // 2-CTA engine: [cta 2][tap 9][w_hi half 32 rows | w_lo half 32 rows][64 ci] fp16, swizzled
@@ -105,6 +106,8 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 void tc_plan_destroy(TcPlan* p);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
+cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
+                                 cudaStream_t st);
 cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
                                 float residual_sign, int clamp, float* out, int variant, cudaStream_t st);

@@ -162,7 +162,11 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const int nimg = (d.B - b0 < h->chunk) ? d.B - b0 : h->chunk;
     const float* cin = in + (size_t)b0 * d.n;
     float* cout = out + (size_t)b0 * d.n;
-    PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
+    if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && !(h->tc_variant & 64)) {
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, st));
+    } else {
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
+    }
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
       // body layers: the 2-CTA (cta_group::2) kernel for large launches, the 1-CTA kernel when there are too few
@@ -601,6 +605,26 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       for (int o = 0; o < co; ++o)
         for (int c = 0; c < ci; ++c)
           for (int tp = 0; tp < 9; ++tp) buf[((size_t)tp * ci + c) * 64 + o] = w[((size_t)o * ci + c) * 9 + tp];
+      {
+        // tcgen05 first layer: rows 0-63 = w_hi[oc], rows 64-127 = w_lo[oc]; half k of a row = weight of (tap, ci) with
+        // k = tap*Cin + ci (< 27), zero beyond; 16-byte chunk j stored at j ^ (row & 7)
+        std::vector<__half> img((size_t)128 * 64, __float2half_rn(0.f));
+        for (int o = 0; o < co; ++o)
+          for (int c = 0; c < ci; ++c)
+            for (int tp = 0; tp < 9; ++tp) {
+              const int kk = tp * ci + c;
+              const float v = w[((size_t)o * ci + c) * 9 + tp];
+              const __half hi = __float2half_rn(v);
+              const __half lo = __float2half_rn(v - __half2float(hi));
+              const int chunk = (kk >> 3) ^ (o & 7);
+              img[(size_t)o * 64 + chunk * 8 + (kk & 7)] = hi;
+              img[(size_t)(64 + o) * 64 + chunk * 8 + (kk & 7)] = lo;
+            }
+        __half* dh = nullptr;
+        PDS_TRY(dev_alloc(h, &dh, img.size()));
+        PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        L.w_first_tc = dh;
+      }
       h->first_w_host = buf;
       h->first_b_host.assign(b, b + co);
       L.w_first_host = h->first_w_host.data();
