@@ -6,10 +6,14 @@
 // Mapping
 //   * one CTA tile = 16 rows x 8 pixels = 128 output pixels = UMMA M; N = 64 output channels;
 //     K = 64 input channels per tap, 9 taps -> 36 k-steps of 16.
-//   * operands are fp16 hi/lo splits (a = a_hi + a_lo, w = w_hi + w_lo); the kernel issues
-//     a_hi*w_hi + a_hi*w_lo + a_lo*w_hi into ONE fp32 TMEM accumulator (108 tcgen05.mma per tile),
-//     which recovers ~2^-22 relative operand precision — needed for the 1e-4 iterate gate
-//     (single-pass fp16 misses it).
+//   * operands are split as a = a_hi + a_lo, w = w_hi + w_lo with a_hi, w_hi fp16.  The leading product
+//     a_hi*w_hi runs as kind::f16 MMAs (K = 64 per tap); the two first-order correction products
+//     a*w_lo + a_lo*w_hi only need ~4 significant bits each, so they run as ONE kind::f8f6f4 MMA per
+//     k-step with K = 128 e4m3 bytes per tap:  A8 = [e4m3(a) | e4m3(a_lo 2^10)],  B8 = [e4m3(w_lo 2^S) | e4m3(w_hi 2^(S-10))]
+//     into a second fp32 TMEM accumulator that the epilogue folds in with the factor 2^-S.
+//     72 tcgen05.mma per tile (was 108 with three fp16 products) at ~2^-16 relative operand precision;
+//     needed for the 1e-4 iterate gate (single-pass fp16 misses it; tools/emulate_split.py
+//     measures 3e-6 for this scheme against 6e-5 for one fp16 pass on the same loop).
 //   * the activation halo tile (18 rows x 10 pixels x 64 ch, one per hi/lo plane) is fetched by
 //     ONE 4-D TMA box each with SWIZZLE_128B; out-of-image pixels are zero-filled by TMA, which is
 //     exactly the convolution's zero padding.  All 9 taps read that single tile: the A descriptor
@@ -17,15 +21,18 @@
 //     (Probed on B200, tests/test_gpu_tcgen05_probe.py: the 128B-swizzle phase is taken from the
 //     shared-memory ADDRESS bits, so any 128-B-aligned start and any SBO multiple of 128 B work with
 //     base_offset = 0.)
-//   * the layer's weights (2 x 9 x 64x64 fp16, pre-swizzled on the host) stay resident in shared
-//     memory for the whole persistent CTA (147 KB), loaded once with cp.async.bulk.
+//   * the layer's weights (9 taps x [64x64 fp16 | 64x128 e4m3], pre-swizzled on the host) stay resident in
+//     shared memory for the whole persistent CTA (147 KB), loaded once with cp.async.bulk.
 //   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected lane,
 //     warp-uniform control flow so descriptors live in uniform registers), warps 2-5 = epilogue
-//     (tcgen05.ld -> bias + LeakyReLU -> hi/lo split -> 16-byte stores).
-//     The accumulator is double-buffered in TMEM (2 x 64 columns) so the epilogue of tile i
-//     overlaps the MMAs of tile i+1; activation planes go through a 3-slot ring (hi_t, lo_t,
-//     hi_t+1, ...) so the producer runs up to three planes ahead of the tensor pipe.
+//     (tcgen05.ld -> bias + LeakyReLU -> fp16 plane + e4m3 plane -> 32-byte stores).
+//     The accumulators are double-buffered in TMEM (2 x 128 columns) so the epilogue of tile i
+//     overlaps the MMAs of tile i+1; activation planes go through a 3-slot ring (p0_t, p1_t,
+//     p0_t+1, ...) so the producer runs up to three planes ahead of the tensor pipe.
+//   Activation layout in HBM: [img][2][H][W][128 B]; plane 0 = fp16(v) x 64 channels, plane 1 =
+//     e4m3(v) x 64 followed by e4m3((v - fp16(v)) * 2^10) x 64.
 #include <cuda.h>
+#include <cuda_fp8.h>
 
 #include "kernels.cuh"
 
@@ -50,10 +57,9 @@ struct Geo {
   static constexpr uint32_t kOffA = kWBytes, kOffBar = kOffA + kSlots * kPlaneSlot;
   static constexpr uint32_t kOffBias = kOffBar + 192, kSmemUsed = kOffBias + 256;
   static constexpr uint32_t kSmemBytes = kSmemUsed + 1024;     // slack for manual 1024-B alignment
-  static constexpr uint32_t kAccCols = 2 * NW;                 // cols [0,NW): a*w_hi ; [NW,2NW): a_hi*w_lo (summed in the epilogue)
+  static constexpr uint32_t kAccCols = 2 * NW;                 // cols [0,NW): a_hi*w_hi (f16 kind) ; [NW,2NW): e4m3 correction (f8f6f4 kind)
   static constexpr uint32_t kTmemCols = 4 * NW < 32 ? 32 : 4 * NW;   // 2 accumulator stages
-  static constexpr uint32_t kIdescLo = kIdescBase | ((uint32_t)(NW >> 3) << 17);
-  static constexpr uint32_t kIdescHi = kIdescBase | ((uint32_t)((2 * NW) >> 3) << 17);
+  static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(NW >> 3) << 17);   // same bits for both kinds: format 0 = F16 / E4M3
 };
 
 struct TcArgs {
@@ -61,6 +67,7 @@ struct TcArgs {
   const float* bias;
   __half* out;            // body layers: next activation buffer
   float slope;
+  float lo_scale;         // 2^-S of this layer's e4m3 correction accumulator
   int H, W, nimg, tiles_x, tiles_y, ntiles;
   int variant;
   // last layer only
@@ -117,6 +124,14 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -145,30 +160,49 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
                : "memory");
 }
 
-// 32 channels [c0, c0+32) of one pixel: v = d0 + d1 + bias -> LeakyReLU -> (hi, lo) fp16, written as full
-// 32-byte sectors (one 256-bit store per 16 channels and plane).
-__device__ __forceinline__ void store_half_row(__half* dst_hi, __half* dst_lo, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
-                                               const float* bias_s, int c0, float slope) {
+constexpr float kActLoScale = 1024.f;     // 2^10: e4m3(a_lo * 2^10) stays finite for |a| < 448 (a_lo <= 2^-11 * 2^ceil(log2|a|))
+
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
+// 32 channels [c0, c0+32) of one pixel: v = d0 + lo_scale*d1 + bias -> LeakyReLU, written as full 32-byte sectors:
+//   plane 0 (dst_p0, fp16 x 64):  fp16(v) at channels c0..c0+31                         (two 256-bit stores)
+//   plane 1 (dst_p1, 128 bytes):  e4m3(v) at byte c0.., e4m3((v - fp16(v)) * 2^10) at byte 64+c0..   (one 256-bit store each)
+__device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
+                                               const float* bias_s, int c0, float slope, float lo_scale) {
+  uint32_t a8[8], l8[8];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
-    uint32_t hi[8], lo[8];
+    uint32_t hi[8];
+    float v[16], l[16];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = q * 16 + 2 * k;
       const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
-      float v0 = (__uint_as_float(d0[c]) + __uint_as_float(d1[c])) + b.x;
-      float v1 = (__uint_as_float(d0[c + 1]) + __uint_as_float(d1[c + 1])) + b.y;
+      float v0 = fmaf(__uint_as_float(d1[c]), lo_scale, __uint_as_float(d0[c])) + b.x;
+      float v1 = fmaf(__uint_as_float(d1[c + 1]), lo_scale, __uint_as_float(d0[c + 1])) + b.y;
       v0 = fmaxf(v0, v0 * slope);            // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
       v1 = fmaxf(v1, v1 * slope);
       const __half2 hh = __floats2half2_rn(v0, v1);
       const float2 hf = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
       hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
+      v[2 * k] = v0;
+      v[2 * k + 1] = v1;
+      l[2 * k] = (v0 - hf.x) * kActLoScale;
+      l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
     }
-    st_global_256(dst_hi + c0 + q * 16, hi);
-    st_global_256(dst_lo + c0 + q * 16, lo);
+    st_global_256(dst_p0 + c0 + q * 16, hi);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a8[q * 4 + k] = pack_e4m3x4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+    }
   }
+  st_global_256(dst_p1 + c0, a8);
+  st_global_256(dst_p1 + 64 + c0, l8);
 }
 
 // Programmatic dependent launch: a layer's CTAs may start (barrier init, TMEM alloc, weight loads) while the
@@ -188,13 +222,13 @@ __device__ __forceinline__ uint32_t elect_one() {
 
 __device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-// All MMAs of one activation plane (36 k-steps).  The weight image keeps, per tap, w_hi (NW rows) directly
-// followed by w_lo (NW rows), so the hi plane multiplies against B = [w_hi ; w_lo] as ONE N=2*NW MMA
-// (columns [0,NW) accumulate a_hi*w_hi, columns [NW,2NW) a_hi*w_lo): the 4 KB A tile is read from shared
-// memory once for two products — the SS-mode MMA is bound by shared-memory operand reads (~100 B/clk
-// measured), so bytes per MAC is what matters.  The lo plane needs only a_lo*w_hi: N=NW into [0,NW).
+// All MMAs of one activation plane (36 k-steps).  The weight image keeps, per tap, the fp16 tile w_hi (NW rows x 128 B)
+// directly followed by the e4m3 tile [w_lo 2^S | w_hi 2^(S-10)] (NW rows x 128 B).  Plane 0 (fp16) accumulates
+// a_hi*w_hi into columns [0,NW) with kind::f16 (K = 16 per MMA); plane 1 (e4m3, 128 K-bytes per pixel and tap)
+// accumulates the correction into columns [NW,2NW) with kind::f8f6f4 (K = 32 per MMA) — the same 32 operand bytes
+// per row and k-step for both, so the descriptor arithmetic is identical.
 // a_lo / w_lo are the low descriptor words of the plane / weight bases; every offset is an immediate.
-template <int NW, bool HI_PLANE>
+template <int NW, bool P0>
 __device__ __forceinline__ void issue_plane(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
   using G = Geo<NW>;
   constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);   // SBO | version 1 | SWIZZLE_128B
@@ -205,9 +239,10 @@ __device__ __forceinline__ void issue_plane(uint32_t d_tmem, uint32_t a_lo, uint
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
-      const uint32_t bo = (uint32_t)(tap * 2 * (int)G::kWTile + k * 32) >> 4;
-      if (HI_PLANE) umma_f16(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), G::kIdescHi, (tap == 0 && k == 0) ? 0u : 1u);
-      else umma_f16(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), G::kIdescLo, 1u);
+      const uint32_t bo = (uint32_t)((tap * 2 + (P0 ? 0 : 1)) * (int)G::kWTile + k * 32) >> 4;
+      const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
+      if (P0) umma_f16(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), G::kIdesc, acc);
+      else umma_f8(d_tmem + NW, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), G::kIdesc, acc);
     }
   }
 }
@@ -331,13 +366,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
         if (y < a.H && x < a.W && !(a.variant & 2)) {     // perf experiment: bit 1 skips the stores
           const size_t pix = (size_t)y * a.W + x;
-          __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-          __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
-          store_half_row(o_hi, o_lo, r0, r2, bias_s, 0, a.slope);
-          store_half_row(o_hi, o_lo, r1, r3, bias_s, 32, a.slope);
+          __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+          uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
+          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
         }
       } else {
-        // last layer: columns [0,16) = a*w_hi, [16,32) = a_hi*w_lo; only the first C are real channels.
+        // last layer: columns [0,16) = a_hi*w_hi, [16,32) = e4m3 correction * 2^S; only the first C are real channels.
         // out = clamp(sign * (conv + bias) + clamp(net_in))   (basic_models.py:36, denoiser.py:40-42, network_dncnn.py:77)
         uint32_t r[32];
         tmem_ld32(taddr, r);
@@ -353,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               const size_t g = ((size_t)img * a.C + c) * hw + pix;
               float xin = __ldg(a.net_in + g);
               if (a.clamp) xin = fminf(fmaxf(xin, 0.f), 1.f);
-              const float n = (__uint_as_float(r[c]) + __uint_as_float(r[16 + c])) + bias_s[c];
+              const float n = fmaf(__uint_as_float(r[16 + c]), a.lo_scale, __uint_as_float(r[c])) + bias_s[c];
               float o = a.res_sign > 0.f ? n + xin : xin - n;
               if (a.clamp) o = fminf(fmaxf(o, 0.f), 1.f);
               a.out_f32[g] = o;
@@ -563,10 +598,10 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
       if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
       if (y < a.H && x < a.W) {
         const size_t pix = (size_t)y * a.W + x;
-        __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-        __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
-        store_half_row(o_hi, o_lo, r0, r2, bias_s, 0, a.slope);
-        store_half_row(o_hi, o_lo, r1, r3, bias_s, 32, a.slope);
+        __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+        uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, 1.f);      // columns [64,128) hold a_hi*w_lo at scale 1
+        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, 1.f);
       }
     }
   }
@@ -583,21 +618,20 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 // 2-CTA variant of the body layer (cta_group::2): a cluster of two CTAs works on two pixel tiles at
 // once as ONE M=256 UMMA issued by CTA 0.  The B operand (weights) is split between the two CTAs'
 // shared memories, so every SM reads only half of B per MMA and keeps only half of the weight image
-// (72 KB instead of 144 KB): the SS-mode MMA is bound by shared-memory operand reads, and this takes
-// the per-tile operand traffic from 504 KB to 396 KB while freeing room for a 5-slot plane ring.
-//   B rows (N = 128, hi plane):  [ w_hi[0:32] ; w_lo[0:32] | w_hi[32:64] ; w_lo[32:64] ]   (CTA 0 | CTA 1)
-//   B rows (N = 64,  lo plane):  [ w_hi[0:32]              | w_hi[32:64]             ]   (first 32 rows of each half)
-//   accumulator columns per stage: [0,32) hh oc<32, [32,64) hl oc<32, [64,96) hh oc>=32, [96,128) hl oc>=32,
-//                                  [128,192) lo-plane a_lo*w_hi for oc 0..63
+// (72 KB instead of 144 KB): the SS-mode MMA at N=64 is bound by shared-memory operand reads (4 KB of A
+// per 32 tensor cycles), so halving the B bytes matters, and the freed room holds a 5-slot plane ring.
+//   per-CTA weight image, per tap: [ fp16 w_hi[32r:32r+32] (4 KB) | e4m3 [w_lo 2^S | w_hi 2^(S-10)][32r:32r+32] (4 KB) ]
+//   B rows (N = 64, either plane):  [ oc 0..31 | oc 32..63 ]   (CTA 0 | CTA 1)
+//   accumulator columns per stage: [0,64) a_hi*w_hi (kind::f16), [64,128) e4m3 correction * 2^S (kind::f8f6f4)
 // ---------------------------------------------------------------------------------------------
 namespace two {
 constexpr uint32_t kWHalf = 9 * 64 * 128;             // 73728: per-CTA weight image
 constexpr int kSlots2 = 5;
 constexpr uint32_t kOffA2 = kWHalf, kOffBar2 = kOffA2 + kSlots2 * kPlaneSlot;
 constexpr uint32_t kOffBias2 = kOffBar2 + 192, kSmemBytes2 = kOffBias2 + 256 + 1024;
-constexpr uint32_t kAccCols2 = 192, kTmemCols2 = 512;
-constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16, M=256
-constexpr uint32_t kIdescN128 = kIdescBase2 | ((128u >> 3) << 17), kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
+constexpr uint32_t kAccCols2 = 128, kTmemCols2 = 256;
+constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16 (or e4m3: same code 0), M=256
+constexpr uint32_t kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
 
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -630,13 +664,21 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, ui
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"((uint16_t)3)
                : "memory");
 }
 
-template <bool HI_PLANE>
+template <bool P0>
 __device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
   constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);
   constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -646,35 +688,11 @@ __device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uin
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
-      const uint32_t bo = (uint32_t)(tap * 8192 + k * 32) >> 4;
-      if (HI_PLANE) umma_f16_2sm(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN128, (tap == 0 && k == 0) ? 0u : 1u);
-      else umma_f16_2sm(d_tmem + 128u, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, (tap == 0 && k == 0) ? 0u : 1u);
+      const uint32_t bo = (uint32_t)(tap * 8192 + (P0 ? 0 : 4096) + k * 32) >> 4;
+      const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
+      if (P0) umma_f16_2sm(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
+      else umma_f8_2sm(d_tmem + 64u, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
     }
-  }
-}
-
-// 32 channels [c0, c0+32) of one pixel from three accumulator pieces.
-__device__ __forceinline__ void store_32ch(__half* dst_hi, __half* dst_lo, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
-                                           const uint32_t (&d2)[32], const float* bias_s, int c0, float slope) {
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = q * 16 + 2 * k;
-      const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
-      float v0 = ((__uint_as_float(d0[c]) + __uint_as_float(d1[c])) + __uint_as_float(d2[c])) + b.x;
-      float v1 = ((__uint_as_float(d0[c + 1]) + __uint_as_float(d1[c + 1])) + __uint_as_float(d2[c + 1])) + b.y;
-      v0 = fmaxf(v0, v0 * slope);
-      v1 = fmaxf(v1, v1 * slope);
-      const __half2 hh = __floats2half2_rn(v0, v1);
-      const float2 hf = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
-      hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[k] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    st_global_256(dst_hi + c0 + q * 16, hi);
-    st_global_256(dst_lo + c0 + q * 16, lo);
   }
 }
 
@@ -795,26 +813,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols2;
       const bool st = live && y < a.H && x < a.W;
       const size_t pix = (size_t)y * a.W + x;
-      __half* o_hi = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-      __half* o_lo = a.out + (((size_t)img * 2 + 1) * hw + pix) * 64;
+      __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+      uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
       {
-        uint32_t r0[32], r1[32], r2[32];
+        uint32_t r0[32], r1[32];
         tmem_ld32(taddr + 0, r0);
-        tmem_ld32(taddr + 32, r1);
-        tmem_ld32(taddr + 128, r2);
+        tmem_ld32(taddr + 64, r1);
         tmem_ld_wait();
-        if (st) store_32ch(o_hi, o_lo, r0, r1, r2, bias_s, 0, a.slope);
+        if (st) store_half_row(o_p0, o_p1, r0, r1, bias_s, 0, a.slope, a.lo_scale);
       }
       {
-        uint32_t r0[32], r1[32], r2[32];
-        tmem_ld32(taddr + 64, r0);
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr + 32, r0);
         tmem_ld32(taddr + 96, r1);
-        tmem_ld32(taddr + 160, r2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);
-        if (st) store_32ch(o_hi, o_lo, r0, r1, r2, bias_s, 32, a.slope);
+        if (st) store_half_row(o_p0, o_p1, r0, r1, bias_s, 32, a.slope, a.lo_scale);
       }
     }
   }
@@ -1026,6 +1042,7 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   a.bias = L.bias;
   a.out = plan->act[in_buf ^ 1];
   a.slope = slope;
+  a.lo_scale = L.lo_scale;
   a.C = 64;
   fill_common(a, plan, nimg, variant);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
@@ -1038,6 +1055,7 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
   a.bias = L.bias;
   a.out = plan->act[in_buf ^ 1];
   a.slope = slope;
+  a.lo_scale = L.lo_scale;
   a.C = 64;
   fill_common(a, plan, nimg, 0);
   const int npairs = (a.ntiles + 1) / 2;
@@ -1077,6 +1095,7 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
   a.C = C;
   a.res_sign = residual_sign;
   a.clamp = clamp;
+  a.lo_scale = L.lo_scale;
   fill_common(a, plan, nimg, variant & 4);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
   return launch_pdl(conv_tc_kernel<16>, grid, kThreads, Geo<16>::kSmemBytes, st, plan->map[in_buf], a);

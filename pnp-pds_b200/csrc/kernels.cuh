@@ -81,16 +81,19 @@ cudaError_t launch_l1ball(const Dims& d, const float* s_in, const float* t, cons
                           float eta_override, float* s_out, float* tau_out /*[B] or null*/, cudaStream_t st);
 
 // ---- dncnn_*.cu ---------------------------------------------------------------
-// Activations between layers: [img][2 (hi,lo)][H][W][64] fp16 ("NHWC hi/lo planes").
+// Activations between layers: [img][2 planes][H][W][128 B] (NHWC).  Plane 0 = fp16(v) x 64 channels in both engines.
+// Plane 1: SIMT engine = fp16(v - fp16(v)) x 64;  tcgen05 engine = e4m3(v) x 64 | e4m3((v - fp16(v)) 2^10) x 64.
+// The two engines never share a buffer.
 struct DncnnLayerW {
   const float* w_first_host;  // HOST [9*Cin][64] (k = tap*Cin + ci): handed to the first-layer kernel by value (constant bank)
   const float* bias_host;     // HOST [64] bias of the first layer
   const __half* w_first_tc;   // tcgen05 first layer: [w_hi 64 rows ; w_lo 64 rows] x 128 B, k = tap*Cin+ci in the first 27 halves, swizzled
   const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
-  const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][2 (hi,lo)][64 oc][64 ci] fp16, 128B-swizzled rows
-  const __half* w_mid_tc2; // 2-CTA engine: [cta 2][tap 9][w_hi half 32 rows | w_lo half 32 rows][64 ci] fp16, swizzled
+  const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][fp16 tile | e4m3 tile][64 oc][128 B], 128B-swizzled rows
+  const __half* w_mid_tc2; // 2-CTA engine: [cta 2][tap 9][fp16 tile 32 rows | e4m3 tile 32 rows][128 B], swizzled
   const float* w_last;    // [Cout][9][64 ci]                            last layer (SIMT engine)
-  const __half* w_last_tc; // [9 taps][2][16 rows][64 ci] fp16 swizzled, rows >= Cout zero   last layer (tcgen05 engine)
+  const __half* w_last_tc; // [9 taps][fp16 tile | e4m3 tile][16 rows][128 B] swizzled, rows >= Cout zero   last layer (tcgen05 engine)
+  float lo_scale;         // 2^-S of the e4m3 correction accumulator (tcgen05 engine, pds_api.cu tc_split_scales)
   const float* bias;      // [Cout of this layer]
 };
 cudaError_t launch_conv_first(int nimg, int C, int H, int W, const float* in /*(nimg,C,H,W)*/, const DncnnLayerW& L, float slope,

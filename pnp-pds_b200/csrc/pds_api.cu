@@ -7,6 +7,9 @@
 #include <new>
 #include <vector>
 
+#include <cmath>
+#include <cuda_fp8.h>
+
 #include "kernels.cuh"
 
 namespace pds {
@@ -90,6 +93,35 @@ int dev_alloc(pds_handle_s* h, T** p, size_t count) {
   return 0;
 }
 
+// Operand split of the tcgen05 engine (dncnn_tc.cu): w = w_hi + w_lo with w_hi fp16; the correction products run in e4m3:
+//   A8 = [e4m3(a) | e4m3(a_lo 2^10)],  B8 = [e4m3(w_lo 2^S) | e4m3(w_hi 2^(S-10))],  correction = 2^-S * (A8 . B8).
+// S is per layer: with max|w| < 2^e,  |w_hi| 2^(S-10) <= 256 and |w_lo| 2^S <= 2^(e-11+S) <= 256 for S = 18 - e.
+struct TcSplit {
+  float s_lo, s_hi;   // 2^S, 2^(S-10)
+  float lo_scale;     // 2^-S
+};
+TcSplit tc_split_scales(const float* w, size_t n) {
+  float m = 0.f;
+  for (size_t i = 0; i < n; ++i) m = std::max(m, std::fabs(w[i]));
+  int e = 0;
+  if (m > 0.f) {
+    std::frexp(m, &e);                 // m = f * 2^e, f in [0.5, 1)  ->  m < 2^e
+  }
+  e = std::max(-20, std::min(e, 14));
+  const int S = 18 - e;
+  return TcSplit{std::ldexp(1.f, S), std::ldexp(1.f, S - 10), std::ldexp(1.f, -S)};
+}
+// One weight w[row][ci] into a fp16 tile and an e4m3 tile (rows of 128 B, 16-byte chunk j of a row stored at j ^ (row & 7)).
+void tc_put_weight(__half* tile16, __half* tile8, int row, int ci, float v, const TcSplit& sp) {
+  const __half hi = __float2half_rn(v);
+  const float lo = v - __half2float(hi);
+  tile16[(size_t)row * 64 + (((ci >> 3) ^ (row & 7)) << 3) + (ci & 7)] = hi;
+  uint8_t* r8 = reinterpret_cast<uint8_t*>(tile8) + (size_t)row * 128;
+  const int k_lo = ci, k_hi = 64 + ci;
+  r8[(((k_lo >> 4) ^ (row & 7)) << 4) + (k_lo & 15)] = (uint8_t)__nv_cvt_float_to_fp8(lo * sp.s_lo, __NV_SATFINITE, __NV_E4M3);
+  r8[(((k_hi >> 4) ^ (row & 7)) << 4) + (k_hi & 15)] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * sp.s_hi, __NV_SATFINITE, __NV_E4M3);
+}
+
 #define PDS_TRY(expr)         \
   do {                        \
     int _r = (expr);          \
@@ -162,7 +194,7 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const int nimg = (d.B - b0 < h->chunk) ? d.B - b0 : h->chunk;
     const float* cin = in + (size_t)b0 * d.n;
     float* cout = out + (size_t)b0 * d.n;
-    if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && !(h->tc_variant & 64)) {
+    if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
@@ -638,19 +670,15 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dw, buf.size()));
       PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
       L.w_last = dw;
-      // tcgen05 engine: [tap][split][16 rows][64 ci] fp16, rows >= Cout are zero, 128B-swizzled rows
+      // tcgen05 engine: [tap][fp16 tile | e4m3 tile][16 rows][128 B], rows >= Cout are zero, 128B-swizzled rows
+      const TcSplit sp = tc_split_scales(w, (size_t)co * ci * 9);
+      L.lo_scale = sp.lo_scale;
       std::vector<__half> img((size_t)9 * 2 * 16 * 64, __float2half_rn(0.f));
       for (int tp = 0; tp < 9; ++tp)
         for (int o = 0; o < co; ++o)
-          for (int c = 0; c < 64; ++c) {
-            const float v = w[((size_t)o * ci + c) * 9 + tp];
-            const __half hi = __float2half_rn(v);
-            const __half lo = __float2half_rn(v - __half2float(hi));
-            const int chunk = (c >> 3) ^ (o & 7);
-            const size_t pos = ((size_t)(tp * 2) * 16 + o) * 64 + chunk * 8 + (c & 7);
-            img[pos] = hi;
-            img[(size_t)16 * 64 + pos] = lo;
-          }
+          for (int c = 0; c < 64; ++c)
+            tc_put_weight(img.data() + (size_t)(tp * 2) * 16 * 64, img.data() + (size_t)(tp * 2 + 1) * 16 * 64, o, c,
+                          w[((size_t)o * ci + c) * 9 + tp], sp);
       __half* dh = nullptr;
       PDS_TRY(dev_alloc(h, &dh, img.size()));
       PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
@@ -665,40 +693,31 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dw, buf.size()));
       PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
       L.w_mid = dw;
-      // tcgen05 engine: shared-memory image [tap][split][oc][ci] fp16 (w_hi rows directly followed by the
-      // w_lo rows of the same tap, so one N=128 descriptor covers both), K-major rows of 128 B,
-      // 16-byte chunk j of row oc stored at chunk (j ^ (oc & 7))  (SWIZZLE_128B)
+      // tcgen05 engine: shared-memory image [tap][fp16 tile | e4m3 tile][oc][128 B]: K-major rows of 128 B,
+      // 16-byte chunk j of row oc stored at chunk (j ^ (oc & 7))  (SWIZZLE_128B).
+      //   fp16 tile row = w_hi[oc][ci 0..63];  e4m3 tile row = [e4m3(w_lo 2^S)[ci 0..63] | e4m3(w_hi 2^(S-10))[ci 0..63]]
+      const TcSplit sp = tc_split_scales(w, (size_t)64 * 64 * 9);
+      L.lo_scale = sp.lo_scale;
       std::vector<__half> img((size_t)2 * 9 * 64 * 64);
       for (int tp = 0; tp < 9; ++tp)
         for (int o = 0; o < 64; ++o)
-          for (int c = 0; c < 64; ++c) {
-            const float v = w[((size_t)o * 64 + c) * 9 + tp];
-            const __half hi = __float2half_rn(v);
-            const __half lo = __float2half_rn(v - __half2float(hi));
-            const int chunk = (c >> 3) ^ (o & 7);
-            const size_t pos = ((size_t)(tp * 2) * 64 + o) * 64 + chunk * 8 + (c & 7);
-            img[pos] = hi;
-            img[(size_t)64 * 64 + pos] = lo;
-          }
+          for (int c = 0; c < 64; ++c)
+            tc_put_weight(img.data() + (size_t)(tp * 2) * 64 * 64, img.data() + (size_t)(tp * 2 + 1) * 64 * 64, o, c,
+                          w[((size_t)o * 64 + c) * 9 + tp], sp);
       __half* dh = nullptr;
       PDS_TRY(dev_alloc(h, &dh, img.size()));
       PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
       L.w_mid_tc = dh;
-      // 2-CTA engine: CTA r keeps, per tap, w_hi[32r:32r+32] followed by w_lo[32r:32r+32] (64 rows of 128 B, swizzled by local row)
+      // 2-CTA engine: CTA r keeps, per tap, the fp16 tile of oc [32r, 32r+32) followed by their e4m3 tile
+      // (2 x 32 rows of 128 B, swizzled by local row)
       std::vector<__half> img2((size_t)2 * 9 * 64 * 64);
       for (int r = 0; r < 2; ++r)
         for (int tp = 0; tp < 9; ++tp)
-          for (int lr = 0; lr < 64; ++lr) {
-            const int o = 32 * r + (lr & 31);
-            const bool is_lo = lr >= 32;
+          for (int lr = 0; lr < 32; ++lr)
             for (int c = 0; c < 64; ++c) {
-              const float v = w[((size_t)o * 64 + c) * 9 + tp];
-              const __half hi = __float2half_rn(v);
-              const __half val = is_lo ? __float2half_rn(v - __half2float(hi)) : hi;
-              const int chunk = (c >> 3) ^ (lr & 7);
-              img2[(((size_t)r * 9 + tp) * 64 + lr) * 64 + chunk * 8 + (c & 7)] = val;
+              __half* t16 = img2.data() + ((size_t)r * 9 + tp) * 64 * 64;
+              tc_put_weight(t16, t16 + 32 * 64, lr, c, w[((size_t)(32 * r + lr) * 64 + c) * 9 + tp], sp);
             }
-          }
       __half* dh2 = nullptr;
       PDS_TRY(dev_alloc(h, &dh2, img2.size()));
       PDS_CUDA_OK(cudaMemcpy(dh2, img2.data(), img2.size() * sizeof(__half), cudaMemcpyHostToDevice));

@@ -9,8 +9,11 @@ pytestmark = pytest.mark.gpu
 
 SIMPLE = ["DnCNN_nobn_nch_1_nlev_0.01", "DnCNN_nobn_nch_3_nlev_0.01", "DnCNN_nobn_nch_1_nlev_0.009"]
 KAIR = [("dncnn_15", 1, 17), ("dncnn_color_blind", 3, 20), ("dncnn3", 1, 20)]
-# fp32 accumulation with activations carried as fp16 hi+lo (2^-22) between 20 layers
+# fp32 accumulation; activations carried between the 20 layers as fp16 hi+lo (2^-22, SIMT engine) or as fp16 plus an
+# e4m3 first-order correction (~2^-16 operand precision, tcgen05 engine; tools/emulate_split.py predicts 2.5e-6..4.4e-6
+# for the simple_CNN checkpoints and 0.9e-5..3.5e-5 for the KAIR ones, against 4.5e-5..1.1e-3 for one plain fp16 pass)
 TOL = 1e-5
+KAIR_TOL = {"simt": 5e-5, "tcgen05": 1e-4}   # no clamps + ReLU: activations an order of magnitude larger than simple_CNN's
 
 
 @pytest.mark.parametrize("engine", ["simt", "tcgen05"])
@@ -40,7 +43,7 @@ def test_kair_dncnn_vs_reference(g_den, arch, ch, nb, engine):
     y = den.denoise_batch(x[None])[0]
     err = float(np.max(np.abs(y - g_den[f"{arch}_y"])))
     print(f"{arch} {engine}: max abs err {err:.3e}")
-    assert err < 5 * TOL        # no clamps + ReLU: activations an order of magnitude larger than simple_CNN's
+    assert err < KAIR_TOL[engine]
 
 
 def test_kair_class_interface(g_den):
