@@ -47,13 +47,12 @@ constexpr uint32_t kPlaneSlot = 23 * 1024;                        // slot stride
 constexpr int kThreads = 192;
 constexpr uint32_t kIdescBase = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((128u >> 4) << 24) /*M=128*/;
 
-// Compile-time geometry for a layer with NW output channels (rows of the B operand per hi/lo split):
-//   NW = 64 : the 64->64 body layers;   NW = 16 : the last layer (Cout = 1|3, zero-padded to 16 rows).
+// Compile-time geometry of a body layer with NW = 64 output channels (rows of the B operand per tile).
 template <int NW>
 struct Geo {
   static constexpr uint32_t kWTile = NW * 128;                 // one (tap, split) NW x 64 fp16 tile
   static constexpr uint32_t kWBytes = 9 * 2 * kWTile;          // 147456 (NW=64) / 36864 (NW=16), 1024-multiples
-  static constexpr int kSlots = NW == 64 ? 3 : 6;              // activation-plane ring depth
+  static constexpr int kSlots = 3;                             // activation-plane ring depth
   static constexpr uint32_t kOffA = kWBytes, kOffBar = kOffA + kSlots * kPlaneSlot;
   static constexpr uint32_t kOffBias = kOffBar + 192, kSmemUsed = kOffBias + 256;
   static constexpr uint32_t kSmemBytes = kSmemUsed + 1024;     // slack for manual 1024-B alignment
@@ -275,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   }
   if (threadIdx.x >= 64 && threadIdx.x < 128) {
     const int c = threadIdx.x - 64;
-    bias_s[c] = (NW == 64 || c < a.C) ? a.bias[c] : 0.f;
+    bias_s[c] = a.bias[c];
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(G::kTmemCols) : "memory");
@@ -354,47 +353,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * G::kAccCols;
-      if constexpr (NW == 64) {
-        uint32_t r0[32], r1[32], r2[32], r3[32];
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 64, r2);
-        tmem_ld32(taddr + 32, r1);
-        tmem_ld32(taddr + 96, r3);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
-        if (y < a.H && x < a.W && !(a.variant & 2)) {     // perf experiment: bit 1 skips the stores
-          const size_t pix = (size_t)y * a.W + x;
-          __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-          uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
-          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
-          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
-        }
-      } else {
-        // last layer: columns [0,16) = a_hi*w_hi, [16,32) = e4m3 correction * 2^S; only the first C are real channels.
-        // out = clamp(sign * (conv + bias) + clamp(net_in))   (basic_models.py:36, denoiser.py:40-42, network_dncnn.py:77)
-        uint32_t r[32];
-        tmem_ld32(taddr, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
-        if (y < a.H && x < a.W) {
-          const size_t pix = (size_t)y * a.W + x;
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            if (c < a.C) {
-              const size_t g = ((size_t)img * a.C + c) * hw + pix;
-              float xin = __ldg(a.net_in + g);
-              if (a.clamp) xin = fminf(fmaxf(xin, 0.f), 1.f);
-              const float n = fmaf(__uint_as_float(r[16 + c]), a.lo_scale, __uint_as_float(r[c])) + bias_s[c];
-              float o = a.res_sign > 0.f ? n + xin : xin - n;
-              if (a.clamp) o = fminf(fmaxf(o, 0.f), 1.f);
-              a.out_f32[g] = o;
-            }
-          }
-        }
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld32(taddr, r0);
+      tmem_ld32(taddr + 64, r2);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld32(taddr + 96, r3);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+      if (y < a.H && x < a.W && !(a.variant & 2)) {     // perf experiment: bit 1 skips the stores
+        const size_t pix = (size_t)y * a.W + x;
+        __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+        uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
+        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
       }
     }
   }
@@ -492,10 +465,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
         if (idx < kWin) {
           const int c = idx / kWinPix, p = idx - c * kWinPix;
           const int gy = y0 + p / kHaloPitch, gx = x0 + p % kHaloPitch;
-          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
-            t = __ldg(a.in + ((size_t)(img * CIN + c) * a.H + gy) * a.W + gx);
-            if (a.clamp_in) t = fminf(fmaxf(t, 0.f), 1.f);
-          }
+          if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) t = __ldg(a.in + ((size_t)(img * CIN + c) * a.H + gy) * a.W + gx);
         }
         r[j] = t;
       }
@@ -513,9 +483,11 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
         const int tile = tile0 + d * gridDim.x;
         if (tile >= a.ntiles) break;
         float* sw = stg + (it & 1) * kWin;
+        // the input clamp (denoiser.py:40) is applied here, kDepth tiles after the load was issued, so that nothing
+        // touches a prefetched register while its load is still in flight
 #pragma unroll
         for (int j = 0; j < PER; ++j)
-          if (m + 128 * j < kWin) sw[m + 128 * j] = pre[d][j];
+          if (m + 128 * j < kWin) sw[m + 128 * j] = a.clamp_in ? fminf(fmaxf(pre[d][j], 0.f), 1.f) : pre[d][j];
         if (tile + kDepth * (int)gridDim.x < a.ntiles) fetch(tile + kDepth * gridDim.x, pre[d]);
         asm volatile("bar.sync 1, 128;" ::: "memory");           // window of this tile complete (4 producer warps)
         float v[32];
@@ -615,6 +587,196 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 }  // namespace first
 
 // ---------------------------------------------------------------------------------------------
+// Last layer (64 -> Cout = 1|3).  With N this small, one MMA group per tap is bound by re-reading the same A tile from
+// shared memory nine times.  Instead the contraction over the 64 input channels is done ONCE per halo pixel for all
+// nine taps at the same time:
+//     P[q][tap*C + c] = sum_ci act[q][ci] * W[c][tap][ci]          q over the 18x10 halo tile,  N = 9*C <= 27 -> 32 columns
+// as two M=128 MMA blocks over the contiguous halo tile (rows 0..127 and rows 52..179), and the epilogue gathers
+//     out[y][x][c] = sum_tap P[(y+dy)*10 + (x+dx)][tap*C + c]  + bias, residual, clamp
+// through a shared-memory copy of P.  16 MMAs per tile instead of 72; the kernel is bound by streaming the activations.
+// Operand split as in the body layers: plane 0 x fp16 w_hi (kind::f16) + plane 1 x e4m3 [w_lo 2^S | w_hi 2^(S-10)] (kind::f8f6f4).
+// ---------------------------------------------------------------------------------------------
+namespace last {
+constexpr int kSlotsL = 6;
+constexpr int kNL = 32;                                   // B rows (tap*C + c), zero beyond 9*C
+constexpr uint32_t kWTileL = kNL * 128, kWBytesL = 2 * kWTileL;   // fp16 tile + e4m3 tile
+constexpr int kHaloPix = kHaloRows * kHaloPitch;          // 180
+constexpr int kBlk1 = kHaloPix - 128;                     // second MMA block starts at halo pixel 52
+constexpr int kPStride = 29;                              // floats per halo pixel in the P copy (odd: conflict-free rows)
+constexpr uint32_t kOffAL = kWBytesL, kOffBarL = kOffAL + kSlotsL * kPlaneSlot;
+constexpr uint32_t kOffBiasL = kOffBarL + 192, kOffPL = kOffBiasL + 64;
+constexpr uint32_t kSmemBytesL = kOffPL + 2 * kHaloPix * kPStride * 4 + 1024;
+constexpr uint32_t kIdescL = kIdescBase | ((uint32_t)(kNL >> 3) << 17);
+
+template <int C>
+__global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sW = base, sA = base + kOffAL, sBar = base + kOffBarL;
+  // barriers: full[6] @0, empty[6] @48, wfull @96, tfull[2] @104, tempty[2] @120, tmem slot @136
+  const uint32_t bFull = sBar, bEmpty = sBar + 48, bW = sBar + 96, bTFull = sBar + 104, bTEmpty = sBar + 120;
+  const uint32_t sTmemSlot = sBar + 136;
+  float* bias_s = reinterpret_cast<float*>(gbase + kOffBiasL);
+  float* P = reinterpret_cast<float*>(gbase + kOffPL);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlotsL; ++i) {
+      mbar_init(bFull + 8 * i, 1);
+      mbar_init(bEmpty + 8 * i, 1);
+    }
+    mbar_init(bW, 1);
+    mbar_init(bTFull, 1); mbar_init(bTFull + 8, 1);
+    mbar_init(bTEmpty, 4); mbar_init(bTEmpty + 8, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + C) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarL + 136);
+  pdl_launch_dependents();
+
+  const int per_img = a.tiles_x * a.tiles_y;
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(bW, kWBytesL);
+      bulk_load(sW, a.w_img, kWBytesL, bW);
+    }
+    __syncwarp();
+    pdl_wait_prior_grid();
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y0 = (rem / a.tiles_x) * kTileRows, x0 = (rem % a.tiles_x) * kTileCols;
+#pragma unroll
+      for (int p = 0; p < 2; ++p, ++j) {
+        const uint32_t slot = j % kSlotsL, use = j / kSlotsL;
+        mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bFull + 8 * slot, kPlaneBytes);
+          tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: 2 planes x 2 row blocks x 4 k-steps
+    mbar_wait(bW, 0);
+    const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
+    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO = 8 contiguous 128-byte rows, SWIZZLE_128B
+    uint32_t j = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+      const uint32_t d_tmem = tmem_base + acc * 128u;
+#pragma unroll
+      for (int p = 0; p < 2; ++p, ++j) {
+        const uint32_t slot = j % kSlotsL, use = j / kSlotsL;
+        mbar_wait(bFull + 8 * slot, use & 1);
+        tc_fence_after();
+        const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+        if (elect_one()) {
+#pragma unroll
+          for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ao = (uint32_t)(b * kBlk1 * 128 + k * 32) >> 4;
+              const uint32_t bo = (uint32_t)(p * (int)kWTileL + k * 32) >> 4;
+              const uint32_t d = d_tmem + (uint32_t)(p * 64 + b * 32);
+              if (p == 0) umma_f16(d, desc64(a_lo + ao, kHi), desc64(w_lo + bo, kHi), kIdescL, k ? 1u : 0u);
+              else umma_f8(d, desc64(a_lo + ao, kHi), desc64(w_lo + bo, kHi), kIdescL, k ? 1u : 0u);
+            }
+          umma_commit(bEmpty + 8 * slot);
+          if (p == 1) umma_commit(bTFull + 8 * acc);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: TMEM -> P (shared) -> 3x3 gather -> planar fp32
+    const int q = warp & 3;
+    const int t = q * 32 + lane;
+    const int ty = t >> 3, tx = t & 7;
+    const size_t hw = (size_t)a.H * a.W;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
+      const uint32_t acc = it & 1;
+      // residual input of this thread's pixel: issued before the wait so its latency hides behind the MMAs
+      const bool live = y < a.H && x < a.W;
+      const size_t pix = (size_t)y * a.W + x;
+      float xin[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) xin[c] = live ? __ldg(a.net_in + ((size_t)img * C + c) * hw + pix) : 0.f;
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
+      float* Pb = P + (it & 1) * (kHaloPix * kPStride);
+      {
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 64, r2);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + 96, r3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+        float* row0 = Pb + t * kPStride;                   // halo pixel t            (block 0)
+#pragma unroll
+        for (int n = 0; n < 9 * C; ++n) row0[n] = fmaf(__uint_as_float(r2[n]), a.lo_scale, __uint_as_float(r0[n]));
+        if (t >= 128 - kBlk1) {                            // halo pixel 52 + t >= 128 (block 1; the rest duplicates block 0)
+          float* row1 = Pb + (kBlk1 + t) * kPStride;
+#pragma unroll
+          for (int n = 0; n < 9 * C; ++n) row1[n] = fmaf(__uint_as_float(r3[n]), a.lo_scale, __uint_as_float(r1[n]));
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // P of this tile complete; also fences the buffer reused two tiles later
+      if (live) {
+        // out = clamp(sign * (conv + bias) + clamp(net_in))   (basic_models.py:36, denoiser.py:40-42, network_dncnn.py:77)
+        float sum[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) sum[c] = bias_s[c];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float* pr = Pb + ((ty + dy) * kHaloPitch + tx + dx) * kPStride + (dy * 3 + dx) * C;
+#pragma unroll
+            for (int c = 0; c < C; ++c) sum[c] += pr[c];
+          }
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float xi = xin[c];
+          if (a.clamp) xi = fminf(fmaxf(xi, 0.f), 1.f);
+          float o = a.res_sign > 0.f ? sum[c] + xi : xi - sum[c];
+          if (a.clamp) o = fminf(fmaxf(o, 0.f), 1.f);
+          a.out_f32[((size_t)img * C + c) * hw + pix] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+}  // namespace last
+
+// ---------------------------------------------------------------------------------------------
 // 2-CTA variant of the body layer (cta_group::2): a cluster of two CTAs works on two pixel tiles at
 // once as ONE M=256 UMMA issued by CTA 0.  The B operand (weights) is split between the two CTAs'
 // shared memories, so every SM reads only half of B per MMA and keeps only half of the weight image
@@ -629,7 +791,8 @@ constexpr uint32_t kWHalf = 9 * 64 * 128;             // 73728: per-CTA weight i
 constexpr int kSlots2 = 5;
 constexpr uint32_t kOffA2 = kWHalf, kOffBar2 = kOffA2 + kSlots2 * kPlaneSlot;
 constexpr uint32_t kOffBias2 = kOffBar2 + 192, kSmemBytes2 = kOffBias2 + 256 + 1024;
-constexpr uint32_t kAccCols2 = 128, kTmemCols2 = 256;
+constexpr uint32_t kAccCols2 = 128, kTmemCols2 = 512;
+constexpr int kAccStages2 = 4;                        // 4 x 128 columns: the epilogue may lag the tensor pipe by three tiles
 constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16 (or e4m3: same code 0), M=256
 constexpr uint32_t kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
 
@@ -646,8 +809,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t ran
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// "TMEM stage drained" signal to the MMA issuer in CTA 0.  Relaxed on purpose: the only accesses it has to follow are this
+// warp's tcgen05.ld (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  A .release arrive at cluster scope
+// compiles to MEMBAR.ALL.GPU, i.e. it waits for every global store the thread has in flight — the activations of the
+// previous tile — which made the epilogue, not the tensor pipe, the pacing stage (ncu: stall_membar 2.0 of 8.3 cycles/inst).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2,
                                                 int c3) {
@@ -703,9 +870,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t sW = base, sA = base + kOffA2, sBar = base + kOffBar2;
-  // barriers: full[5] @0 (used in CTA 0), empty[5] @40, wfull @80, tfull[2] @88, tempty[2] @104 (CTA 0), tmem slot @120
-  const uint32_t bFull = sBar, bEmpty = sBar + 40, bW = sBar + 80, bTFull = sBar + 88, bTEmpty = sBar + 104;
-  const uint32_t sTmemSlot = sBar + 120;
+  // barriers: full[5] @0 (used in CTA 0), empty[5] @40, wfull @80, tfull[4] @88, tempty[4] @120 (CTA 0), tmem slot @152
+  const uint32_t bFull = sBar, bEmpty = sBar + 40, bW = sBar + 80, bTFull = sBar + 88, bTEmpty = sBar + 120;
+  const uint32_t sTmemSlot = sBar + 152;
   float* bias_s = reinterpret_cast<float*>(gbase + kOffBias2);
   const uint32_t rank = cluster_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -716,8 +883,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       mbar_init(bEmpty + 8 * i, 1);         // multicast commit from CTA 0
     }
     mbar_init(bW, 1);
-    mbar_init(bTFull, 1); mbar_init(bTFull + 8, 1);
-    mbar_init(bTEmpty, 8); mbar_init(bTEmpty + 8, 8);   // 4 epilogue warps x 2 CTAs arrive on CTA 0's barrier
+    for (int i = 0; i < kAccStages2; ++i) {
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 8);        // 4 epilogue warps x 2 CTAs arrive on CTA 0's barrier
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
   }
@@ -741,7 +910,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   __syncthreads();
   cluster_sync_all();                       // ... and the peer's too; all barriers of both CTAs are initialised
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar2 + 120);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBar2 + 152);
   pdl_launch_dependents();
 
   const int per_img = a.tiles_x * a.tiles_y;
@@ -774,8 +943,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       uint32_t j = 0;
       int it = 0;
       for (int pair = cid; pair < npairs; pair += nclusters, ++it) {
-        const uint32_t acc = it & 1;
-        mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+        const uint32_t acc = it % kAccStages2;
+        mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it / kAccStages2) & 1) ^ 1));
         const uint32_t d_tmem = tmem_base + acc * kAccCols2;
 #pragma unroll
         for (int p = 0; p < 2; ++p, ++j) {
@@ -807,30 +976,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int tl = live ? tile : a.ntiles - 1;
       const int img = tl / per_img, rem = tl - img * per_img;
       const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
-      const uint32_t acc = it & 1;
-      mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
+      const uint32_t acc = it % kAccStages2;
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it / kAccStages2) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols2;
       const bool st = live && y < a.H && x < a.W;
       const size_t pix = (size_t)y * a.W + x;
       __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
       uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr + 0, r0);
-        tmem_ld32(taddr + 64, r1);
-        tmem_ld_wait();
-        if (st) store_half_row(o_p0, o_p1, r0, r1, bias_s, 0, a.slope, a.lo_scale);
-      }
-      {
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr + 32, r0);
-        tmem_ld32(taddr + 96, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);
-        if (st) store_half_row(o_p0, o_p1, r0, r1, bias_s, 32, a.slope, a.lo_scale);
+      uint32_t r0[32], r1[32], r2[32], r3[32];
+      tmem_ld32(taddr + 0, r0);
+      tmem_ld32(taddr + 64, r2);
+      tmem_ld32(taddr + 32, r1);
+      tmem_ld32(taddr + 96, r3);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);      // stage released before any arithmetic or store
+      if (st) {
+        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
+        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
       }
     }
   }
@@ -989,7 +1154,9 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   if (!rc) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<64>::kSmemBytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<16>::kSmemBytes);
+      e = cudaFuncSetAttribute(last::conv_last_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)last::kSmemBytesL);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(last::conv_last_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)last::kSmemBytesL);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(two::conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)two::kSmemBytes2);
     if (e == cudaSuccess)
@@ -1096,9 +1263,11 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
   a.res_sign = residual_sign;
   a.clamp = clamp;
   a.lo_scale = L.lo_scale;
-  fill_common(a, plan, nimg, variant & 4);
+  fill_common(a, plan, nimg, 0);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  return launch_pdl(conv_tc_kernel<16>, grid, kThreads, Geo<16>::kSmemBytes, st, plan->map[in_buf], a);
+  if (C == 1) return launch_pdl(last::conv_last_tc_kernel<1>, grid, kThreads, last::kSmemBytesL, st, plan->map[in_buf], a);
+  if (C == 3) return launch_pdl(last::conv_last_tc_kernel<3>, grid, kThreads, last::kSmemBytesL, st, plan->map[in_buf], a);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace pds

@@ -670,15 +670,15 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dw, buf.size()));
       PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
       L.w_last = dw;
-      // tcgen05 engine: [tap][fp16 tile | e4m3 tile][16 rows][128 B], rows >= Cout are zero, 128B-swizzled rows
+      // tcgen05 engine: [fp16 tile | e4m3 tile][32 rows][128 B]; B row n = tap*Cout + c holds W[c][tap][ci 0..63]
+      // (all nine taps side by side along N, dncnn_tc.cu namespace last), rows >= 9*Cout are zero, 128B-swizzled rows
       const TcSplit sp = tc_split_scales(w, (size_t)co * ci * 9);
       L.lo_scale = sp.lo_scale;
-      std::vector<__half> img((size_t)9 * 2 * 16 * 64, __float2half_rn(0.f));
+      std::vector<__half> img((size_t)2 * 32 * 64, __float2half_rn(0.f));
       for (int tp = 0; tp < 9; ++tp)
         for (int o = 0; o < co; ++o)
           for (int c = 0; c < 64; ++c)
-            tc_put_weight(img.data() + (size_t)(tp * 2) * 16 * 64, img.data() + (size_t)(tp * 2 + 1) * 16 * 64, o, c,
-                          w[((size_t)o * ci + c) * 9 + tp], sp);
+            tc_put_weight(img.data(), img.data() + (size_t)32 * 64, tp * co + o, c, w[((size_t)o * ci + c) * 9 + tp], sp);
       __half* dh = nullptr;
       PDS_TRY(dev_alloc(h, &dh, img.size()));
       PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
