@@ -31,21 +31,12 @@
 //     p0_t+1, ...) so the producer runs up to three planes ahead of the tensor pipe.
 //   Activation layout in HBM: [img][2][H][W][128 B]; plane 0 = fp16(v) x 64 channels, plane 1 =
 //     e4m3(v) x 64 followed by e4m3((v - fp16(v)) * 2^10) x 64.
-#include <cuda.h>
-#include <cuda_fp8.h>
-
-#include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace pds {
 
 namespace {
 
-constexpr int kTileRows = 16, kTileCols = 8;          // output tile (M = 128)
-constexpr int kHaloRows = 18, kHaloPitch = 10;        // pixels
-constexpr uint32_t kPlaneBytes = kHaloRows * kHaloPitch * 128;   // 23040 bytes landed by one TMA box
-constexpr uint32_t kPlaneSlot = 23 * 1024;                        // slot stride: keeps every slot 1024-B aligned
-constexpr int kThreads = 192;
-constexpr uint32_t kIdescBase = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((128u >> 4) << 24) /*M=128*/;
 
 // Compile-time geometry of a body layer with NW = 64 output channels (rows of the B operand per tile).
 template <int NW>
@@ -61,165 +52,7 @@ struct Geo {
   static constexpr uint32_t kIdesc = kIdescBase | ((uint32_t)(NW >> 3) << 17);   // same bits for both kinds: format 0 = F16 / E4M3
 };
 
-struct TcArgs {
-  const __half* w_img;
-  const float* bias;
-  __half* out;            // body layers: next activation buffer
-  float slope;
-  float lo_scale;         // 2^-S of this layer's e4m3 correction accumulator
-  int H, W, nimg, tiles_x, tiles_y, ntiles;
-  int variant;
-  // last layer only
-  const float* net_in;    // (nimg, C, H, W) network input (residual)
-  float* out_f32;         // (nimg, C, H, W)
-  int C;
-  float res_sign;
-  int clamp;
-};
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!ok && spin > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor").
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t base_off) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)(base_off & 7u) << 49) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
-               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
-
-constexpr float kActLoScale = 1024.f;     // 2^10: e4m3(a_lo * 2^10) stays finite for |a| < 448 (a_lo <= 2^-11 * 2^ceil(log2|a|))
-
-__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
-  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
-  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
-  return lo | (hi << 16);
-}
-
-// 32 channels [c0, c0+32) of one pixel: v = d0 + lo_scale*d1 + bias -> LeakyReLU, written as full 32-byte sectors:
-//   plane 0 (dst_p0, fp16 x 64):  fp16(v) at channels c0..c0+31                         (two 256-bit stores)
-//   plane 1 (dst_p1, 128 bytes):  e4m3(v) at byte c0.., e4m3((v - fp16(v)) * 2^10) at byte 64+c0..   (one 256-bit store each)
-__device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
-                                               const float* bias_s, int c0, float slope, float lo_scale) {
-  uint32_t a8[8], l8[8];
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    uint32_t hi[8];
-    float v[16], l[16];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = q * 16 + 2 * k;
-      const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
-      float v0 = fmaf(__uint_as_float(d1[c]), lo_scale, __uint_as_float(d0[c])) + b.x;
-      float v1 = fmaf(__uint_as_float(d1[c + 1]), lo_scale, __uint_as_float(d0[c + 1])) + b.y;
-      v0 = fmaxf(v0, v0 * slope);            // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
-      v1 = fmaxf(v1, v1 * slope);
-      const __half2 hh = __floats2half2_rn(v0, v1);
-      const float2 hf = __half22float2(hh);
-      hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      v[2 * k] = v0;
-      v[2 * k + 1] = v1;
-      l[2 * k] = (v0 - hf.x) * kActLoScale;
-      l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
-    }
-    st_global_256(dst_p0 + c0 + q * 16, hi);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      a8[q * 4 + k] = pack_e4m3x4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-      l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
-    }
-  }
-  st_global_256(dst_p1 + c0, a8);
-  st_global_256(dst_p1 + 64 + c0, l8);
-}
-
-// Programmatic dependent launch: a layer's CTAs may start (barrier init, TMEM alloc, weight loads) while the
-// previous layer's grid is still draining; everything that touches the previous layer's output waits here.
-__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-__device__ __forceinline__ uint32_t elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred;
-}
-
-__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // All MMAs of one activation plane (36 k-steps).  The weight image keeps, per tap, the fp16 tile w_hi (NW rows x 128 B)
 // directly followed by the e4m3 tile [w_lo 2^S | w_hi 2^(S-10)] (NW rows x 128 B).  Plane 0 (fp16) accumulates
@@ -796,54 +629,6 @@ constexpr int kAccStages2 = 4;                        // 4 x 128 columns: the ep
 constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16 (or e4m3: same code 0), M=256
 constexpr uint32_t kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
 
-__device__ __forceinline__ uint32_t cluster_rank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-// "TMEM stage drained" signal to the MMA issuer in CTA 0.  Relaxed on purpose: the only accesses it has to follow are this
-// warp's tcgen05.ld (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  A .release arrive at cluster scope
-// compiles to MEMBAR.ALL.GPU, i.e. it waits for every global store the thread has in flight — the activations of the
-// previous tile — which made the epilogue, not the tensor pipe, the pacing stage (ncu: stall_membar 2.0 of 8.3 cycles/inst).
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2,
-                                                int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f8_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-               "h"((uint16_t)3)
-               : "memory");
-}
 
 template <bool P0>
 __device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
@@ -1112,12 +897,12 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W) {
+int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W, int box_w, int box_h) {
   EncodeTiledFn enc = get_encode();
   PDS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg * 2};
   const cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
-  const cuuint32_t box[4] = {64, (cuuint32_t)kHaloPitch, (cuuint32_t)kHaloRows, 1};
+  const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, act, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1127,12 +912,6 @@ int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W) {
 
 }  // namespace
 
-struct TcPlan {
-  CUtensorMap map[2];
-  __half* act[2];
-  int nimg, H, W;
-  int num_sms;
-};
 
 int tc_num_sms() {
   int dev = 0, n = 148;
@@ -1149,8 +928,11 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   p->H = H;
   p->W = W;
   p->num_sms = tc_num_sms();
-  int rc = make_act_map(&p->map[0], act0, nimg, H, W);
-  if (!rc) rc = make_act_map(&p->map[1], act1, nimg, H, W);
+  int rc = make_act_map(&p->map[0], act0, nimg, H, W, kHaloPitch, kHaloRows);
+  if (!rc) rc = make_act_map(&p->map[1], act1, nimg, H, W, kHaloPitch, kHaloRows);
+  if (!rc) rc = make_act_map(&p->map_row[0], act0, nimg, H, W, 130, 1);      // dncnn_roll.cu: 128-pixel strip + x halo
+  if (!rc) rc = make_act_map(&p->map_row[1], act1, nimg, H, W, 130, 1);
+  if (!rc) rc = roll_setup();
   if (!rc) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<64>::kSmemBytes);
     if (e == cudaSuccess)
@@ -1178,21 +960,6 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-template <typename Kern, typename... Args>
-static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, args...);
-}
-
 static void fill_common(TcArgs& a, TcPlan* plan, int nimg, int variant) {
   a.H = plan->H;
   a.W = plan->W;
@@ -1216,7 +983,7 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   return launch_pdl(conv_tc_kernel<64>, grid, kThreads, Geo<64>::kSmemBytes, st, plan->map[in_buf], a);
 }
 
-cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st) {
+cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st) {
   TcArgs a{};
   a.w_img = L.w_mid_tc2;
   a.bias = L.bias;
@@ -1224,7 +991,7 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
   a.slope = slope;
   a.lo_scale = L.lo_scale;
   a.C = 64;
-  fill_common(a, plan, nimg, 0);
+  fill_common(a, plan, nimg, variant);
   const int npairs = (a.ntiles + 1) / 2;
   const int nclusters = npairs < plan->num_sms / 2 ? npairs : plan->num_sms / 2;
   return launch_pdl(two::conv_tc2_kernel, 2 * nclusters, kThreads, two::kSmemBytes2, st, plan->map[in_buf], a);
@@ -1292,7 +1059,7 @@ extern "C" int pds_debug_umma_probe(unsigned a_off, unsigned sbo, unsigned base_
 extern "C" int pds_debug_tma_probe(const void* act_dev, int nimg, int H, int W, int x, int y, int plane_index, void* out_host) {
   using namespace pds;
   CUtensorMap map;
-  int rc = make_act_map(&map, (__half*)act_dev, nimg, H, W);
+  int rc = make_act_map(&map, (__half*)act_dev, nimg, H, W, kHaloPitch, kHaloRows);
   if (rc) return rc;
   uint4* d = nullptr;
   PDS_CUDA_OK(cudaMalloc(&d, kPlaneBytes));

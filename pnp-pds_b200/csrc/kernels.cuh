@@ -111,9 +111,13 @@ void tc_plan_destroy(TcPlan* p);
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
 cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
                                  cudaStream_t st);
-cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
+cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
                                 float residual_sign, int clamp, float* out, int variant, cudaStream_t st);
 int tc_num_sms();
+// row-streaming body layer (dncnn_roll.cu): band height for a launch of nimg images (0 = not applicable, use the tile kernels)
+int roll_setup();
+int roll_band_rows(int nimg, int H, int W, int num_sms);
+cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, cudaStream_t st);
 
 }  // namespace pds

@@ -122,6 +122,11 @@ void tc_put_weight(__half* tile16, __half* tile8, int row, int ci, float v, cons
   r8[(((k_hi >> 4) ^ (row & 7)) << 4) + (k_hi & 15)] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * sp.s_hi, __NV_SATFINITE, __NV_E4M3);
 }
 
+int tc_num_sms_cached() {
+  static int n = tc_num_sms();
+  return n;
+}
+
 #define PDS_TRY(expr)         \
   do {                        \
     int _r = (expr);          \
@@ -201,12 +206,16 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     }
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
-      // body layers: the 2-CTA (cta_group::2) kernel for large launches, the 1-CTA kernel when there are too few
-      // tiles to fill CTA pairs evenly (single small images); PDS_TC_VARIANT bit 4 / bit 5 force 1-CTA / 2-CTA
+      // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and the launch
+      // has enough row bands for every CTA pair; else the 2-CTA tile kernel for large launches and the 1-CTA tile kernel
+      // for single small images.  PDS_TC_VARIANT bit 7 disables row streaming, bit 4 / bit 5 force 1-CTA / 2-CTA tiles.
       const long long ntiles = (long long)nimg * ((d.H + 15) / 16) * ((d.W + 7) / 8);
+      const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached());
       const bool two_cta = (h->tc_variant & 32) || (!(h->tc_variant & 16) && ntiles >= 4096);
-      if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {
-        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
+      if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && band > 0) {
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, st));
+      } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
       } else {
@@ -925,7 +934,9 @@ int pds_profile_read(pds_handle_t h, double* ms_out, long long* count_out, int r
 long long pds_kernel_launches(pds_handle_t h) { return h ? h->launches : -1; }
 size_t pds_workspace_bytes(pds_handle_t h) { return h ? h->bytes : 0; }
 
-/* test hook: select the tcgen05 descriptor variant (see dncnn_tc.cu) */
+int pds_debug_roll_band_rows(int nimg, int H, int W) { return pds::roll_band_rows(nimg, H, W, pds::tc_num_sms()); }
+
+/* test hook: perf-experiment switches of the tcgen05 engine (see run_dncnn) */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant) {
   if (!h) return 1;
   h->tc_variant = variant;

@@ -1,0 +1,282 @@
+// Device-side building blocks shared by the tcgen05 kernels (dncnn_tc.cu, dncnn_roll.cu): mbarrier / TMA / tcgen05 PTX
+// wrappers, the K-major SWIZZLE_128B descriptor helpers, the activation epilogue (fp16 plane + e4m3 plane) and the
+// launch plan.  Everything is internal to the library (anonymous namespace: one copy per translation unit).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp8.h>
+
+#include "kernels.cuh"
+
+namespace pds {
+
+// Tensor maps and geometry of the two activation buffers of one engine handle.
+struct TcPlan {
+  CUtensorMap map[2];       // halo-tile boxes (64 ch x 10 px x 18 rows) for the 16x8-pixel tile kernels
+  CUtensorMap map_row[2];   // row boxes (64 ch x 130 px x 1 row) for the row-streaming body kernel
+  __half* act[2];
+  int nimg, H, W;
+  int num_sms;
+};
+
+namespace {
+
+constexpr int kTileRows = 16, kTileCols = 8;          // output tile (M = 128)
+constexpr int kHaloRows = 18, kHaloPitch = 10;        // pixels
+constexpr uint32_t kPlaneBytes = kHaloRows * kHaloPitch * 128;   // 23040 bytes landed by one TMA box
+constexpr uint32_t kPlaneSlot = 23 * 1024;                        // slot stride: keeps every slot 1024-B aligned
+constexpr int kThreads = 192;
+constexpr uint32_t kIdescBase = (1u << 4) /*D=f32*/ | (0u << 7) /*A=f16*/ | (0u << 10) /*B=f16*/ | ((128u >> 4) << 24) /*M=128*/;
+
+struct TcArgs {
+  const __half* w_img;
+  const float* bias;
+  __half* out;            // body layers: next activation buffer
+  float slope;
+  float lo_scale;         // 2^-S of this layer's e4m3 correction accumulator
+  int H, W, nimg, tiles_x, tiles_y, ntiles;
+  int variant;
+  // last layer only
+  const float* net_in;    // (nimg, C, H, W) network input (residual)
+  float* out_f32;         // (nimg, C, H, W)
+  int C;
+  float res_sign;
+  int clamp;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor").
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t base_off) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)(base_off & 7u) << 49) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
+constexpr float kActLoScale = 1024.f;     // 2^10: e4m3(a_lo * 2^10) stays finite for |a| < 448 (a_lo <= 2^-11 * 2^ceil(log2|a|))
+
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return lo | (hi << 16);
+}
+
+// 32 channels [c0, c0+32) of one pixel: v = d0 + lo_scale*d1 + bias -> LeakyReLU, written as full 32-byte sectors:
+//   plane 0 (dst_p0, fp16 x 64):  fp16(v) at channels c0..c0+31                         (two 256-bit stores)
+//   plane 1 (dst_p1, 128 bytes):  e4m3(v) at byte c0.., e4m3((v - fp16(v)) * 2^10) at byte 64+c0..   (one 256-bit store each)
+__device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
+                                               const float* bias_s, int c0, float slope, float lo_scale) {
+  uint32_t a8[8], l8[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t hi[8];
+    float v[16], l[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = q * 16 + 2 * k;
+      const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
+      float v0 = fmaf(__uint_as_float(d1[c]), lo_scale, __uint_as_float(d0[c])) + b.x;
+      float v1 = fmaf(__uint_as_float(d1[c + 1]), lo_scale, __uint_as_float(d0[c + 1])) + b.y;
+      v0 = fmaxf(v0, v0 * slope);            // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
+      v1 = fmaxf(v1, v1 * slope);
+      const __half2 hh = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hh);
+      hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      v[2 * k] = v0;
+      v[2 * k + 1] = v1;
+      l[2 * k] = (v0 - hf.x) * kActLoScale;
+      l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
+    }
+    st_global_256(dst_p0 + c0 + q * 16, hi);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      a8[q * 4 + k] = pack_e4m3x4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+    }
+  }
+  st_global_256(dst_p1 + c0, a8);
+  st_global_256(dst_p1 + 64 + c0, l8);
+}
+
+// Programmatic dependent launch: a layer's CTAs may start (barrier init, TMEM alloc, weight loads) while the
+// previous layer's grid is still draining; everything that touches the previous layer's output waits here.
+__device__ __forceinline__ void pdl_wait_prior_grid() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+// ---- cta_group::2 (CTA pair) variants --------------------------------------------------------
+namespace two {
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// "TMEM stage drained" signal to the MMA issuer in CTA 0.  Relaxed on purpose: the only accesses it has to follow are this
+// warp's tcgen05.ld (ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync).  A .release arrive at cluster scope
+// compiles to MEMBAR.ALL.GPU, i.e. it waits for every global store the thread has in flight — the activations of the
+// previous tile — which made the epilogue, not the tensor pipe, the pacing stage (ncu: stall_membar 2.0 of 8.3 cycles/inst).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1, int c2,
+                                                int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f8_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// kind / collector usage as template parameters (COLL: 0 none, 1 collector::a::fill, 2 collector::a::use, 3 collector::a::lastuse).
+// The A collector keeps the A tile of the previous MMA inside the tensor core: consecutive MMAs with the same A descriptor
+// then read it from shared memory once (measured with ncu: l1tex tc wavefronts drop by exactly the A share).
+template <bool F16, int COLL>
+__device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+#define PDS_MMA2(KIND, C)                                                                                              \
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"                                                     \
+               "tcgen05.mma.cta_group::2.kind::" KIND C " [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), \
+               "r"(idesc), "r"(accumulate)                                                                             \
+               : "memory")
+  if constexpr (F16) {
+    if constexpr (COLL == 0) PDS_MMA2("f16", "");
+    else if constexpr (COLL == 1) PDS_MMA2("f16", ".collector::a::fill");
+    else if constexpr (COLL == 2) PDS_MMA2("f16", ".collector::a::use");
+    else PDS_MMA2("f16", ".collector::a::lastuse");
+  } else {
+    if constexpr (COLL == 0) PDS_MMA2("f8f6f4", "");
+    else if constexpr (COLL == 1) PDS_MMA2("f8f6f4", ".collector::a::fill");
+    else if constexpr (COLL == 2) PDS_MMA2("f8f6f4", ".collector::a::use");
+    else PDS_MMA2("f8f6f4", ".collector::a::lastuse");
+  }
+#undef PDS_MMA2
+}
+}  // namespace two
+
+// ---- host: launch with programmatic stream serialization (PDL) -------------------------------
+template <typename Kern, typename... Args>
+static cudaError_t launch_pdl(Kern kern, int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+}  // namespace
+}  // namespace pds
