@@ -363,7 +363,7 @@ def main():
     # ---- end to end through the host-buffer C-ABI call (H2D of x0/obs/x_true + loop + D2H of x and traces)
     def e2e_call(n_it):
         t = time.perf_counter()
-        x, s, tr = eng.restore_host(h_x0.numpy(), h_obs.numpy(), h_true.numpy(), n_it, want_s=False)
+        x, s, tr = eng.restore_host(h_x0.numpy(), h_obs.numpy(), h_true.numpy(), n_it, want_s=False, out=h_out.numpy())
         torch.cuda.synchronize(dev)
         return time.perf_counter() - t, tr
     e2e_call(1)
@@ -385,6 +385,15 @@ def main():
         mid_ms, mid_n = prof["conv_mid"]
         chunk = min(B, a.chunk or max(1, (8 << 20) // (H * W)))
         n_mid_layers = weights.depth - 2
+        # which body-layer kernel the library dispatches for this launch shape (pds_api.cu run_dncnn)
+        if a.engine != "tcgen05":
+            mid_kernel = "conv_mid_simt_kernel"
+        elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W) > 0:
+            mid_kernel = "roll::conv_roll_kernel (row-streaming cta_group::2 body layer, %d-row bands)" % eng.lib.pds_debug_roll_band_rows(int(chunk), H, W)
+        elif chunk * ((H + 15) // 16) * ((W + 7) // 8) >= 4096:
+            mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
+        else:
+            mid_kernel = "conv_tc_kernel<64> (1-CTA tile kernel)"
         total_flop = DNCNN_FLOP_PER_PX_MID_LAYER * float(B * H * W) * n_mid_layers * a.steps
         achieved = total_flop / (mid_ms * 1e-3) / 1e12 if mid_n else None
         # DRAM traffic of the body-layer kernel per launch, from the committed ncu --set full capture (bytes per pixel x
@@ -413,8 +422,8 @@ def main():
             gpu_launches=int(launches),
             clocks=sampler.result(),
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=3 * nbytes, d2h_bytes_per_step=nbytes + a.e2e_iters * B * 4 * 8,
-                     iterations_per_call=a.e2e_iters, api="pds_restore_host (host buffers in, host buffers out)"),
-            roofline=dict(bound="tensor", kernel="conv_mid_tc_kernel" if a.engine == "tcgen05" else "conv_mid_simt_kernel",
+                     iterations_per_call=a.e2e_iters, api="pds_restore_host (pinned host buffers in, pinned host buffer out)"),
+            roofline=dict(bound="tensor", kernel=mid_kernel,
                           achieved=achieved, peak=pk["tensor"], unit="TFLOP/s", frac=(achieved / pk["tensor"]) if achieved else None,
                           traffic=traffic, algorithmic_bytes_per_launch=512.0 * chunk * H * W,
                           issued_tflops_fp16_equiv=(2.0 * achieved) if (achieved and a.engine == "tcgen05") else None,
@@ -424,8 +433,8 @@ def main():
                           measured="CUDA events around each launch, second pass of the same %d steps (%.3f ms/step with events)" % (a.steps, ms_prof / a.steps),
                           note="algorithmic FLOPs = 73728 per pixel per layer (counted once).  Each algorithmic MAC is issued as one fp16 MAC "
                                "(a_hi*w_hi) plus two e4m3 MACs (a*w_lo + a_lo*w_hi, one K=128 kind::f8f6f4 MMA at twice the fp16 rate) = two "
-                               "fp16-MAC times (issued_tflops_fp16_equiv), so frac <= 1/2 by construction; at N=64 the SS-mode MMA is bound "
-                               "by shared-memory operand reads (ncu: l1tex tc wavefronts 89% of peak) and the board runs at its power cap (see clocks)"),
+                               "fp16-MAC times (issued_tflops_fp16_equiv), so frac <= 1/2 by construction; the board runs at its power cap (see clocks) "
+                               "and the layer also moves 512 B/pixel through HBM (profiles/: ~4.4 TB/s while the kernel runs)"),
             roofline_hbm=(dict(bound="hbm", kernel="dual_pw_kernel (fused Phi + over-relaxation + l2-ball/l1 terms + metrics), ours-B / random_sampling",
                                achieved=probe["dual"]["gbs"], peak=pk["hbm"], unit="GB/s", frac=probe["dual"]["gbs"] / pk["hbm"],
                                primal_achieved=probe["primal"]["gbs"], primal_frac=probe["primal"]["gbs"] / pk["hbm"],

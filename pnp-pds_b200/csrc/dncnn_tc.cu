@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+      if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
       if (y < a.H && x < a.W && !(a.variant & 2)) {     // perf experiment: bit 1 skips the stores
         const size_t pix = (size_t)y * a.W + x;
         __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
@@ -221,12 +221,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 // kernel is bound by writing the 256 B/pixel of activations, not by CUDA-core FMAs.
 // ---------------------------------------------------------------------------------------------
 namespace first {
-constexpr int kStages = 4, kThreadsF = 320;                 // 4 producer warps, 1 MMA warp, 4 epilogue warps, 1 spare
+constexpr int kStages = 4, kThreadsF = 544;                 // 2 x 4 producer warps, 1 MMA warp, 2 x 4 epilogue warps
+constexpr int kMmaWarpF = 8;
 constexpr uint32_t kWBytesF = 128 * 128;                    // [w_hi 64 rows ; w_lo 64 rows] x 128 B
 constexpr uint32_t kATile = 128 * 128;                      // one plane of one stage
 constexpr uint32_t kOffAF = kWBytesF, kOffBarF = kOffAF + kStages * 2 * kATile;
 constexpr uint32_t kOffBiasF = kOffBarF + 192, kOffStgF = kOffBiasF + 256;
-constexpr uint32_t kSmemBytesF = kOffStgF + 2 * 18 * 10 * 3 * 4 + 1024;       // + double-buffered input window (Cin <= 3)
+constexpr uint32_t kSmemBytesF = kOffStgF + 4 * 18 * 10 * 3 * 4 + 1024;       // + double-buffered input window per producer group (Cin <= 3)
 constexpr uint32_t kIdescN64 = kIdescBase | ((64u >> 3) << 17), kIdescN128 = kIdescBase | ((128u >> 3) << 17);
 
 struct FirstArgs {
@@ -260,8 +261,8 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
     mbar_init(bTEmpty, 4); mbar_init(bTEmpty + 8, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x >= 160 && threadIdx.x < 224) bias_s[threadIdx.x - 160] = a.bias[threadIdx.x - 160];
-  if (warp == 4) {
+  if (threadIdx.x >= 288 && threadIdx.x < 352) bias_s[threadIdx.x - 288] = a.bias[threadIdx.x - 288];
+  if (warp == kMmaWarpF) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -276,18 +277,20 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
   const int per_img = a.tiles_x * a.tiles_y;
   const size_t hw = (size_t)a.H * a.W;
 
-  if (warp < 4) {
-    // ------------------------------------------------------------ im2col producers (thread m = pixel m of the tile)
+  if (warp < kMmaWarpF) {
+    // ------------------------------------------------------------ im2col producers (thread m = pixel m of the tile).  Two groups of
+    // four warps; group g builds the tiles with it % 2 == g (its own staging window, named barrier and A stages g, g+2).
     if (threadIdx.x == 0) {
       mbar_expect_tx(bW, kWBytesF);
       bulk_load(sW, a.w_img, kWBytesF, bW);
     }
-    const int m = threadIdx.x, ty = m >> 3, tx = m & 7;
+    const int grp = warp >> 2;
+    const int m = threadIdx.x & 127, ty = m >> 3, tx = m & 7;
     // The (18 x 10 x Cin) input window of a tile is fetched cooperatively (each of the 128 producer threads loads
     // PER elements, coalesced along x), kDepth tiles ahead of its use so DRAM latency is off the critical path,
     // staged through a double-buffered shared-memory window, and then every thread gathers its own 3x3xCin patch.
     constexpr int kWinPix = kHaloRows * kHaloPitch, kWin = kWinPix * CIN, PER = (kWin + 127) / 128, kDepth = 3;
-    float* stg = reinterpret_cast<float*>(gbase + kOffStgF);           // [2][kWin]
+    float* stg = reinterpret_cast<float*>(gbase + kOffStgF);           // [2 groups][2][kWin]
     auto fetch = [&](int tile, float (&r)[PER]) {
       const int img = tile / per_img, rem = tile - img * per_img;
       const int y0 = (rem / a.tiles_x) * kTileRows - 1, x0 = (rem % a.tiles_x) * kTileCols - 1;
@@ -304,25 +307,26 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
       }
     };
     float pre[kDepth][PER];
+    const int tstep = 2 * (int)gridDim.x;                         // tile stride of this group's sequence
 #pragma unroll
     for (int d = 0; d < kDepth; ++d) {
-      const int t0 = blockIdx.x + d * gridDim.x;
+      const int t0 = blockIdx.x + grp * (int)gridDim.x + d * tstep;
       if (t0 < a.ntiles) fetch(t0, pre[d]);
     }
-    int it = 0;
-    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += kDepth * gridDim.x) {
+    int it = grp;
+    for (int tile0 = blockIdx.x + grp * (int)gridDim.x; tile0 < a.ntiles; tile0 += kDepth * tstep) {
 #pragma unroll
-      for (int d = 0; d < kDepth; ++d, ++it) {
-        const int tile = tile0 + d * gridDim.x;
+      for (int d = 0; d < kDepth; ++d, it += 2) {
+        const int tile = tile0 + d * tstep;
         if (tile >= a.ntiles) break;
-        float* sw = stg + (it & 1) * kWin;
+        float* sw = stg + (grp * 2 + ((it >> 1) & 1)) * kWin;
         // the input clamp (denoiser.py:40) is applied here, kDepth tiles after the load was issued, so that nothing
         // touches a prefetched register while its load is still in flight
 #pragma unroll
         for (int j = 0; j < PER; ++j)
           if (m + 128 * j < kWin) sw[m + 128 * j] = a.clamp_in ? fminf(fmaxf(pre[d][j], 0.f), 1.f) : pre[d][j];
-        if (tile + kDepth * (int)gridDim.x < a.ntiles) fetch(tile + kDepth * gridDim.x, pre[d]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");           // window of this tile complete (4 producer warps)
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // window of this tile complete (the group's 4 warps)
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         float v[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) v[k] = 0.f;
@@ -353,9 +357,12 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
       }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(bFull + 8 * stage);
+        // prefetch for the tile kDepth rounds ahead — issued AFTER the releasing arrive above, whose MEMBAR would otherwise wait
+        // for these loads to return and expose the full DRAM latency on every tile
+        if (tile + kDepth * tstep < a.ntiles) fetch(tile + kDepth * tstep, pre[d]);
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == kMmaWarpF) {
     // ------------------------------------------------------------ MMA issuer
     mbar_wait(bW, 0);
     const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
@@ -379,40 +386,48 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
       }
       __syncwarp();
     }
-  } else if (warp < 9) {
-    // ------------------------------------------------------------ epilogue (same as the body layers)
-    const int q = warp & 3;
+  } else {
+    // ------------------------------------------------------------ epilogue: two groups of four warps (the epilogue of a tile is a
+    // ~700-instruction dependent chain per thread and this layer has almost no tensor work to hide it behind); group g drains
+    // the tiles with it % 2 == g, which are exactly the tiles of accumulator stage g
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+    const int grp = (warp - (kMmaWarpF + 1)) >> 2;
     const int m = q * 32 + lane;
     const int ty = m >> 3, tx = m & 7;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    int it = grp;
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, it += 2) {
       const int img = tile / per_img, rem = tile - img * per_img;
       const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
-      const uint32_t acc = it & 1;
+      const uint32_t acc = (uint32_t)grp;
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      tmem_ld32(taddr, r0);
-      tmem_ld32(taddr + 64, r2);
-      tmem_ld32(taddr + 32, r1);
-      tmem_ld32(taddr + 96, r3);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
-      if (y < a.H && x < a.W) {
-        const size_t pix = (size_t)y * a.W + x;
-        __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-        uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
-        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, 1.f);      // columns [64,128) hold a_hi*w_lo at scale 1
-        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, 1.f);
+      const bool st = y < a.H && x < a.W;
+      const size_t pix = (size_t)y * a.W + x;
+      __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+      uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+      {
+        uint32_t r0[32], r2[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 64, r2);
+        tmem_ld_wait();
+        if (st) store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, 1.f);      // columns [64,128) hold a_hi*w_lo at scale 1
+      }
+      {
+        uint32_t r1[32], r3[32];
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + 96, r3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
+        if (st) store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, 1.f);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarpF) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
@@ -565,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bTEmpty + 8 * acc);
+        if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
         float* row0 = Pb + t * kPStride;                   // halo pixel t            (block 0)
 #pragma unroll
         for (int n = 0; n < 9 * C; ++n) row0[n] = fmaf(__uint_as_float(r2[n]), a.lo_scale, __uint_as_float(r0[n]));

@@ -54,6 +54,12 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// "TMEM stage drained" signal: the only accesses it has to follow are the warp's tcgen05.ld (ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync), so no release fence is needed — the default .release arrive compiles to a MEMBAR that
+// waits for every global load / store the thread still has in flight.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 // Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;

@@ -218,11 +218,18 @@ class Engine:
             _lib.check(self.lib.pds_get_traces(self._h, out.ctypes.data_as(C.c_void_p), out.size, self._stream()))
         return out
 
-    def restore_host(self, x0: np.ndarray, obs: np.ndarray, x_true: np.ndarray | None, n_iter: int, want_s: bool = True):
-        """Whole job through host buffers (H2D + loop + D2H inside the C call)."""
+    def restore_host(self, x0: np.ndarray, obs: np.ndarray, x_true: np.ndarray | None, n_iter: int, want_s: bool = True,
+                     out: np.ndarray | None = None):
+        """Whole job through host buffers (H2D + loop + D2H inside the C call).  `out`: optional caller-owned float32
+        buffer of the batch shape for the result (e.g. pinned memory, which the device copies into at full PCIe speed)."""
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32).reshape(self.shape)
         x0, obs, x_true = f(x0), f(obs), f(x_true)
-        x = np.empty(self.shape, dtype=np.float32)
+        if out is not None:
+            if out.dtype != np.float32 or not out.flags.c_contiguous or out.size != int(np.prod(self.shape)):
+                raise ValueError("out must be a C-contiguous float32 array of the batch shape")
+            x = out.reshape(self.shape)
+        else:
+            x = np.empty(self.shape, dtype=np.float32)
         s = np.empty(self.shape, dtype=np.float32) if want_s else None
         tr = np.zeros((int(n_iter), self.B, TRACE_WIDTH), dtype=np.float64)
         hp = lambda a: C.c_void_p(0) if a is None else a.ctypes.data_as(C.c_void_p)
