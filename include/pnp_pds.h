@@ -43,7 +43,11 @@ enum {
   PDS_METHOD_RED = 4, /* A-RED-DnCNN / comparisonA-6 : iteration.py:100-105 */
   PDS_METHOD_ADMM_B2 = 5, /* comparisonB-2 : iteration.py:127-132 + algorithm/admm.py:30-44 */
   PDS_METHOD_ADMM_C = 6,  /* C-PnPADMM-DnCNN / comparisonC-2 : iteration.py:161-165 + admm.py:4-16 */
-  PDS_METHOD_RED_C = 7    /* C-RED-DnCNN / comparisonC-3 : iteration.py:166-172 + admm.py:4-28 */
+  PDS_METHOD_RED_C = 7,   /* C-RED-DnCNN / comparisonC-3 : iteration.py:166-172 + admm.py:4-28 */
+  /* TV baselines (no denoiser; colour images only, as the reference's D / D_T, operators.py:117-137) */
+  PDS_METHOD_TV_A = 8,    /* A-PDS-TV / comparisonA-4 : iteration.py:88-94 */
+  PDS_METHOD_TV_B3 = 9,   /* comparisonB-3 : iteration.py:133-140 */
+  PDS_METHOD_TV_FBS = 10  /* A-FBS-TV : iteration.py:95-99 */
 };
 
 /* engine used for the 64->64 channel layers of the denoiser */

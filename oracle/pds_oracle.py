@@ -183,6 +183,47 @@ def grad_s_l2(x, s, phi, x_0):
 
 
 # --------------------------------------------------------------------------
+# Total-variation pieces of the TV baselines  (reference operators.py:110-137; colour images only — the
+# reference hard-codes three channels)
+# --------------------------------------------------------------------------
+
+
+def tv_D(x: np.ndarray) -> np.ndarray:
+    """operators.py:117-125: forward differences, (3,H,W) -> (6,H,W) = [vertical (axis 1); horizontal (axis 2)], last row /
+    column zero."""
+    C, H, W = x.shape
+    out = np.zeros((2 * C, H, W))
+    out[:C, :H - 1, :] = x[:, 1:, :] - x[:, :-1, :]
+    out[C:, :, :W - 1] = x[:, :, 1:] - x[:, :, :-1]
+    return out
+
+
+def tv_DT(y: np.ndarray) -> np.ndarray:
+    """operators.py:127-137.  The exact adjoint of tv_D except in the last row / column, where the reference returns
+    +y[last] instead of +y[last-1].  Restated as written."""
+    C = y.shape[0] // 2
+    v, h = y[:C], y[C:]
+    H, W = v.shape[1], v.shape[2]
+    xv = np.empty(v.shape)
+    xv[:, 0, :] = -v[:, 0, :]
+    xv[:, 1:H - 1, :] = -v[:, 1:H - 1, :] + v[:, 0:H - 2, :]
+    xv[:, H - 1, :] = v[:, H - 1, :]
+    xh = np.empty(h.shape)
+    xh[:, :, 0] = -h[:, :, 0]
+    xh[:, :, 1:W - 1] = -h[:, :, 1:W - 1] + h[:, :, 0:W - 2]
+    xh[:, :, W - 1] = h[:, :, W - 1]
+    return xv + xh
+
+
+def prox_l12(x: np.ndarray, gamma: float) -> np.ndarray:
+    """operators.py:110-112: group soft-threshold over axis 0 (all six difference channels of a pixel together)."""
+    nrm = np.sqrt(np.sum(x * x, 0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        val = gamma / nrm
+    return np.fmax(1 - val, 0) * x
+
+
+# --------------------------------------------------------------------------
 # DnCNN denoiser  (reference models/denoiser.py:34-46, models/basic_models.py:25-38,
 #                  models/network_dncnn.py:42-77)
 # --------------------------------------------------------------------------
@@ -401,7 +442,7 @@ def synthetic_image(b: int, C: int, H: int, W: int) -> np.ndarray:
 METHOD_ALIASES = {
     "ours-A": "A-Proposed", "ours-B": "B-Proposed", "ours-C": "C-Proposed",
     "comparisonA-1": "A-PnPFBS-DnCNN", "comparisonA-6": "A-RED-DnCNN",
-    "comparisonC-2": "C-PnPADMM-DnCNN", "comparisonC-3": "C-RED-DnCNN",
+    "comparisonC-2": "C-PnPADMM-DnCNN", "comparisonC-3": "C-RED-DnCNN", "comparisonA-4": "A-PDS-TV",
 }
 
 
@@ -420,6 +461,7 @@ def pds_iterations(x_0, x_obsrv, x_true, phi, adj_phi, denoise, gamma1, gamma2, 
     s = np.zeros(x_0.shape) if s0 is None else s0
     z = np.zeros(x_0.shape)
     d = np.zeros(x_0.shape)
+    y1 = np.concatenate([np.zeros(x_0.shape), np.zeros(x_0.shape)], 0)     # iteration.py:25 (TV baselines)
     c = np.zeros(max_iter)
     psnr = np.zeros(max_iter)
     snaps = {}
@@ -469,6 +511,23 @@ def pds_iterations(x_0, x_obsrv, x_true, phi, adj_phi, denoise, gamma1, gamma2, 
         elif method == "comparisonB-5":                              # iteration.py:146-149
             x = denoise(x - gamma1 * grad_x_l2(x, s, phi, adj_phi, x_obsrv))
             s = proj_l1_ball(s - gamma1 * grad_s_l2(x, s, phi, x_obsrv), alpha_s, sp_nl)
+        elif method == "A-PDS-TV":                                   # iteration.py:88-94 (y plays the role of y2_n)
+            x = x - gamma1 * (tv_DT(y1) + adj_phi(y))
+            y1 = y1 + gamma2 * tv_D(2 * x - x_prev)
+            y1 = y1 - gamma2 * prox_l12(y1 / gamma2, 1 / gamma2)
+            y = y + gamma2 * phi(2 * x - x_prev)
+            y = y - gamma2 * proj_l2_ball(y / gamma2, alpha_n, gaussian_nl, sp_nl, x_obsrv)
+        elif method == "A-FBS-TV":                                   # iteration.py:95-99
+            x = x - gamma1 * (adj_phi(phi(x) - x_obsrv) + tv_DT(y1))
+            y1 = y1 + gamma2 * tv_D(2 * x - x_prev)
+            y1 = y1 - gamma2 * prox_l12(y1 / gamma2, 1 / gamma2)
+        elif method == "comparisonB-3":                              # iteration.py:133-140 (both projections WITHOUT r)
+            x = x - gamma1 * (tv_DT(y1) + adj_phi(y))
+            s = proj_l1_ball(s - gamma1 * y, alpha_s, sp_nl)
+            y1 = y1 + gamma2 * tv_D(2 * x - x_prev)
+            y1 = y1 - gamma2 * prox_l12(y1 / gamma2, 1 / gamma2)
+            y = y + gamma2 * (phi(2 * x - x_prev) + 2 * s - s_prev)
+            y = y - gamma2 * proj_l2_ball(y / gamma2, alpha_n, gaussian_nl, sp_nl, x_obsrv)
         elif method in ("C-PnPADMM-DnCNN", "C-RED-DnCNN"):          # iteration.py:161-172, admm.py:4-28
             xx = np.ones(d.shape)
             ones_adj = adj_phi(np.ones(xx.shape))

@@ -12,7 +12,7 @@ from . import _build
 
 _lib = None
 
-METHODS = {"A": 0, "B": 1, "C": 2, "FBS": 3, "RED": 4, "ADMM_B2": 5, "ADMM_C": 6, "RED_C": 7}
+METHODS = {"A": 0, "B": 1, "C": 2, "FBS": 3, "RED": 4, "ADMM_B2": 5, "ADMM_C": 6, "RED_C": 7, "TV_A": 8, "TV_B3": 9, "TV_FBS": 10}
 DEG_OPS = {"Id": 0, "blur": 1, "random_sampling": 2}
 CONV_ENGINES = {"tcgen05": 0, "simt": 1}
 TRACE_WIDTH = 5

@@ -71,6 +71,11 @@ cudaError_t launch_blur_apply(const Dims& d, const BlurTaps& taps, int adjoint, 
 cudaError_t launch_primal_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);
 cudaError_t launch_dual_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);
 
+// ---- pds_tv.cu: TV baselines (C = 3) --------------------------------------------
+// xn = u - gamma1 * D_T(y1);   y1 <- unit-ball projection per pixel of y1 + gamma2 * D(2 xn - x)     (y1: (B,6,H,W))
+cudaError_t launch_tv_primal(const Dims& d, const float* u, const float* y1, const ItemParams* prm, float* xn, cudaStream_t st);
+cudaError_t launch_tv_dual(const Dims& d, const float* xn, const float* x, const ItemParams* prm, float* y1, cudaStream_t st);
+
 // ---- pds_ssim.cu ---------------------------------------------------------------
 cudaError_t launch_ssim(const Dims& d, const float* xtrue, const float* x, unsigned* mm, double* sums_cur, cudaStream_t st);
 

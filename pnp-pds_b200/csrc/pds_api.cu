@@ -30,6 +30,7 @@ struct pds_handle_s {
   float* obs = nullptr;
   float* xtrue = nullptr;
   float* tmp[2] = {nullptr, nullptr};
+  float* y1 = nullptr;       // TV baselines: dual variable of the difference operator, (B, 6, H, W)
   // ADMM cross-check loops (algorithm/admm.py): z, d, work buffers, adj_phi(ones), coefficient table
   float* zbuf = nullptr;
   float* dbuf = nullptr;
@@ -242,10 +243,17 @@ int post_iteration(pds_handle_s* h, const float* x_new, cudaStream_t st) {
   return 0;
 }
 
+// which of the A / B / C update rules the fused primal / dual kernels apply for this handle's method
+int kernel_method(const pds_handle_s* h) {
+  if (h->cfg.method == PDS_METHOD_TV_A) return PDS_METHOD_A;
+  if (h->cfg.method == PDS_METHOD_TV_B3) return PDS_METHOD_B;
+  return h->cfg.method;
+}
+
 StepArgs step_args(pds_handle_s* h) {
   StepArgs a{};
   a.d = h->d;
-  a.method = h->cfg.method;
+  a.method = kernel_method(h);
   a.x = h->xbuf[h->cur];
   a.xn = h->xbuf[h->cur ^ 1];
   a.u = h->u;
@@ -294,6 +302,9 @@ __global__ void fbs_combine_kernel(Dims d, const float* __restrict__ x, const fl
     if (mode == 0) {
       // iteration.py:73: x - gamma1*myLambda*0.5*(2 Phi^T(Phi x - b))
       out[g] = fmaf(-p.g1 * p.lam, v[g], x[g]);
+    } else if (mode == 2) {
+      // iteration.py:97 (A-FBS-TV): x - gamma1 * Phi^T(Phi x - b); the D_T(y1) term is added by tv_primal
+      out[g] = fmaf(-p.g1, v[g], x[g]);
     } else {
       // iteration.py:102-105: mu = 2/(1/g1^2 + lam); x - mu*((1/g1^2) Phi^T(Phi x - b) + lam (x - D(x)))
       const float ig = 1.f / (p.g1 * p.g1);
@@ -335,6 +346,48 @@ int fbs_red_iteration(pds_handle_s* h, cudaStream_t st) {
   return 0;
 }
 
+
+// TV baselines: A-PDS-TV (iteration.py:88-94), comparisonB-3 (iteration.py:133-140), A-FBS-TV (iteration.py:95-99).
+// The y2 / s updates are those of A-/B-Proposed (same fused kernels, lazy l2-ball scaling); the denoiser is replaced by
+// x+ = u - gamma1 D_T(y1), followed by the y1 update.
+int tv_iteration(pds_handle_s* h, cudaStream_t st) {
+  const Dims& d = h->d;
+  StepArgs a = step_args(h);
+  float* x = h->xbuf[h->cur];
+  float* xn = h->xbuf[h->cur ^ 1];
+  const bool blur = h->cfg.deg_op == PDS_OP_BLUR;
+  if (h->cfg.method == PDS_METHOD_TV_FBS) {
+    // u = x - gamma1 Phi^T(Phi x - b)
+    const size_t n = total_elems(h);
+    PDS_TRY(apply_phi(h, false, x, h->tmp[0], st));
+    PDS_LAUNCH(h, launch_axpbypcz(n, 1.f, h->tmp[0], -1.f, h->obs, 0.f, nullptr, h->tmp[0], st));
+    if (h->cfg.deg_op == PDS_OP_ID) PDS_CUDA_OK(cudaMemcpyAsync(h->tmp[1], h->tmp[0], n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else PDS_TRY(apply_phi(h, true, h->tmp[0], h->tmp[1], st));
+    dim3 grid((d.n + 1023) / 1024 > 148 * 4 ? 148 * 4 : (d.n + 1023) / 1024, d.B);
+    fbs_combine_kernel<<<grid, 256, 0, st>>>(d, x, h->tmp[1], h->prm, 2, nullptr, h->u);
+    PDS_LAUNCH(h, cudaGetLastError());
+  } else {
+    // u = x - gamma1 Phi^T y2 ;  s+ = P_l1(s - gamma1 y2)
+    if (blur) PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_blur(a, h->taps, st));
+    else PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_pointwise(a, st));
+    if (h->cfg.method == PDS_METHOD_TV_B3)
+      PDS_LAUNCH_P(h, PDS_PROF_L1BALL, st, launch_l1ball(d, a.s_old, h->t, h->prm, a.sums_prev, -1.f, h->sbuf[h->scur ^ 1], nullptr, st));
+  }
+  PDS_LAUNCH(h, launch_tv_primal(d, h->u, h->y1, h->prm, xn, st));
+  PDS_LAUNCH(h, launch_tv_dual(d, xn, x, h->prm, h->y1, st));
+  if (h->cfg.method == PDS_METHOD_TV_FBS) {
+    const size_t row = (size_t)d.B * NSUM;
+    PDS_LAUNCH(h, launch_metrics(d, xn, x, h->have_true ? h->xtrue : nullptr, h->sums + (size_t)h->iter * row, st));
+  } else {
+    if (blur) PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_blur(a, h->taps, st));
+    else PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_pointwise(a, st));
+  }
+  PDS_TRY(post_iteration(h, xn, st));
+  h->cur ^= 1;
+  if (h->cfg.method == PDS_METHOD_TV_B3) h->scur ^= 1;
+  h->iter++;
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // ADMM cross-check loops (algorithm/admm.py, iteration.py:127-132,161-172).
@@ -494,7 +547,9 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   PDS_REQUIRE(cfg && out, "null argument");
   PDS_REQUIRE(cfg->batch >= 1 && cfg->height >= 1 && cfg->width >= 1, "bad shape");
   PDS_REQUIRE(cfg->channels == 1 || cfg->channels == 3, "channels must be 1 or 3 (reference ch)");
-  PDS_REQUIRE(cfg->method >= PDS_METHOD_A && cfg->method <= PDS_METHOD_RED_C, "unknown method");
+  PDS_REQUIRE(cfg->method >= PDS_METHOD_A && cfg->method <= PDS_METHOD_TV_FBS, "unknown method");
+  PDS_REQUIRE(cfg->method < PDS_METHOD_TV_A || (cfg->channels == 3 && cfg->height >= 2 && cfg->width >= 2),
+              "the TV baselines are defined for colour images only (operators.py:122-123)");
   PDS_REQUIRE(cfg->deg_op >= PDS_OP_ID && cfg->deg_op <= PDS_OP_RANDOM_SAMPLING, "unknown deg_op");
   PDS_REQUIRE(cfg->max_iter >= 1, "max_iter must be >= 1");
   PDS_REQUIRE((long long)cfg->batch * cfg->channels <= 65535, "batch*channels exceeds the grid limit");
@@ -517,7 +572,11 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   A(&h->obs, n); A(&h->xtrue, n);
   if (cfg->method == PDS_METHOD_B) { A(&h->sbuf[0], n); A(&h->sbuf[1], n); }
   if (cfg->method == PDS_METHOD_FBS || cfg->method == PDS_METHOD_RED) { A(&h->tmp[0], n); A(&h->tmp[1], n); }
-  if (cfg->method >= PDS_METHOD_ADMM_B2) {
+  if (cfg->method >= PDS_METHOD_TV_A) {
+    A(&h->y1, 2 * n);
+    if (cfg->method == PDS_METHOD_TV_B3) { A(&h->sbuf[0], n); A(&h->sbuf[1], n); }
+    if (cfg->method == PDS_METHOD_TV_FBS) { A(&h->tmp[0], n); A(&h->tmp[1], n); }
+  } else if (cfg->method >= PDS_METHOD_ADMM_B2) {
     A(&h->zbuf, n); A(&h->dbuf, n); A(&h->wrk[0], n); A(&h->wrk[1], n); A(&h->wrk[2], n); A(&h->ones_adj, n);
     A(&h->coef, (size_t)8 * cfg->batch * 6);
     if (cfg->method == PDS_METHOD_ADMM_B2 && !h->sbuf[0]) { A(&h->sbuf[0], n); A(&h->sbuf[1], n); }
@@ -802,6 +861,7 @@ int pds_set_problem(pds_handle_t h, const float* x0, const float* obs, const flo
   h->have_true = xtrue != nullptr;
   if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyDeviceToDevice, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->t, 0, nb, st));
+  if (h->y1) PDS_CUDA_OK(cudaMemsetAsync(h->y1, 0, 2 * nb, st));
   if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
   h->have_problem = true;
@@ -818,6 +878,7 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
     h->ssim_now = h->ssim_mode == 1 || (h->ssim_mode == 2 && i == n_iter - 1);
     if (h->cfg.method <= PDS_METHOD_C) PDS_TRY(pds_iteration(h, st));
     else if (h->cfg.method <= PDS_METHOD_RED) PDS_TRY(fbs_red_iteration(h, st));
+    else if (h->cfg.method >= PDS_METHOD_TV_A) PDS_TRY(tv_iteration(h, st));
     else {
       PDS_TRY(admm_prepare(h, st));
       if (h->cfg.method == PDS_METHOD_ADMM_B2) PDS_TRY(admm_b2_iteration(h, st));
@@ -859,7 +920,7 @@ int pds_get_state(pds_handle_t h, float* x, float* s, float* y, pds_stream_t str
   if (y) {
     const size_t row = (size_t)h->d.B * NSUM;
     const double* sums = h->iter > 0 ? h->sums + (size_t)(h->iter - 1) * row : nullptr;
-    if (h->cfg.method <= PDS_METHOD_B) PDS_LAUNCH(h, launch_scale_by_sigma(h->d, h->t, h->prm, sums, h->cfg.method, y, st));
+    if (kernel_method(h) <= PDS_METHOD_B) PDS_LAUNCH(h, launch_scale_by_sigma(h->d, h->t, h->prm, sums, kernel_method(h), y, st));
     else PDS_CUDA_OK(cudaMemcpyAsync(y, h->t, nb, cudaMemcpyDeviceToDevice, st));
   }
   return 0;
@@ -888,6 +949,7 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
   h->have_true = xtrue != nullptr;
   if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyHostToDevice, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->t, 0, nb, st));
+  if (h->y1) PDS_CUDA_OK(cudaMemsetAsync(h->y1, 0, 2 * nb, st));
   if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
   h->have_problem = true;

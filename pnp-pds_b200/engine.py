@@ -23,6 +23,7 @@ METHOD_ALIASES = {
     "comparisonA-7": "A-PnPPDS-unstable-DnCNN", "comparisonC-4": "C-PnP-unstable-DnCNN",
     "comparisonC-2": "C-PnPADMM-DnCNN", "comparisonC-3": "C-RED-DnCNN",
     "comparisonA-2": "A-PnPPDS-BM3D", "comparisonC-1": "C-PnPPDS-BM3D",
+    "comparisonA-4": "A-PDS-TV",                       # ideas/param_memo.py:21-26 (gamma1 = 0.1: the TV primal-dual baseline)
 }
 RESIDENT_METHODS = {
     "A-Proposed": "A", "B-Proposed": "B", "C-Proposed": "C",
@@ -31,7 +32,10 @@ RESIDENT_METHODS = {
     "comparisonB-2": "ADMM_B2", "C-PnPADMM-DnCNN": "ADMM_C", "C-RED-DnCNN": "RED_C",
     # the "unstable" KAIR variants run the same PDS loop with a different denoiser epilogue
     "A-PnPPDS-unstable-DnCNN": "A", "C-PnP-unstable-DnCNN": "C",
+    # TV baselines: no denoiser, colour images only (iteration.py:88-99,133-140)
+    "A-PDS-TV": "TV_A", "A-FBS-TV": "TV_FBS", "comparisonB-3": "TV_B3",
 }
+DENOISER_FREE = {"TV_A", "TV_FBS", "TV_B3"}
 
 
 def canonical_method(method: str) -> str:

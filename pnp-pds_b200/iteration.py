@@ -11,7 +11,7 @@ from typing import Sequence
 
 import numpy as np
 
-from .engine import (RESIDENT_METHODS, Engine, canonical_method, l1_ball_radius, l2_ball_radius, metrics_from_traces,
+from .engine import (DENOISER_FREE, RESIDENT_METHODS, Engine, canonical_method, l1_ball_radius, l2_ball_radius, metrics_from_traces,
                      ssim_from_traces)
 from .models.weights import DnCNNWeights, load_weights
 from .operators import ObservationOperator, sampling_mask
@@ -19,7 +19,6 @@ from .utils.utils_eval import eval_ssim
 
 _OUT_OF_SCOPE = {
     "A-PnPPDS-BM3D", "A-PnPFBS-BM3D", "comparisonB-1", "C-PnPPDS-BM3D",      # need the bm3d wheel (CPU-only algorithm)
-    "A-PDS-TV", "A-FBS-TV", "comparisonB-3",                                   # TV baselines, no denoiser
 }
 _NO_REFERENCE_BEHAVIOUR = {"comparisonB-4", "comparisonB-5"}   # the reference dies with UnboundLocalError (iteration.py:40,143,148)
 
@@ -40,7 +39,8 @@ def item_params(method_id: str, n: int, gamma1, gamma2, alpha_s, alpha_n, myLamb
     to proj_l2_ball (iteration.py:52) so epsilon uses r = 1; B-Proposed passes r to both projections
     (iteration.py:56,58)."""
     r_l2 = r if method_id == "B" else 1.0
-    r_l1 = 1.0 if method_id == "ADMM_B2" else r       # comparisonB-2 calls both projections without r (iteration.py:131, admm.py:43)
+    # comparisonB-2 and comparisonB-3 call both projections without r (iteration.py:131,135,140, admm.py:43)
+    r_l1 = 1.0 if method_id in ("ADMM_B2", "TV_B3") else r
     return dict(gamma1=gamma1, gamma2=gamma2, epsilon=l2_ball_radius(n, alpha_n, gaussian_nl, sp_nl, r_l2),
                 eta=l1_ball_radius(n, alpha_s, sp_nl, r_l1), lam=myLambda, alpha=poisson_alpha)
 
@@ -53,7 +53,7 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
     Returns dict(x, s, c, psnr, ssim, time_per_iter, traces, launches)."""
     name = canonical_method(method)
     if name in _OUT_OF_SCOPE:
-        raise ValueError(f"method {method!r} is outside the B200 hot path (BM3D / TV baselines, see DESIGN.md)")
+        raise ValueError(f"method {method!r} is outside the B200 hot path (BM3D baselines, see DESIGN.md)")
     if name in _NO_REFERENCE_BEHAVIOUR:
         raise NotImplementedError(f"method {method!r} cannot run in the reference either (denoiser_J is never constructed for it)")
     if name not in RESIDENT_METHODS:
@@ -67,7 +67,12 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
     if C != ch:
         raise ValueError(f"ch={ch} but the images have {C} channels")
     n = C * H * W
-    weights = path_prox if isinstance(path_prox, DnCNNWeights) else load_weights(str(path_prox))
+    if mid in DENOISER_FREE:
+        if C != 3:
+            raise ValueError(f"'{name}' is defined for colour images only (operators.py:122-123 hard-code three channels)")
+        weights = None                                               # path_prox is ignored, as in the reference (iteration.py:34-41)
+    else:
+        weights = path_prox if isinstance(path_prox, DnCNNWeights) else load_weights(str(path_prox))
     if "unstable" in name:
         nb = 20 if ch == 3 else 17                                   # iteration.py:34-39
         if weights.depth != nb or weights.residual_sign > 0:
@@ -88,7 +93,8 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         eng.set_params(items)
         if mid in ("ADMM_B2", "ADMM_C", "RED_C"):
             eng.set_admm(m1, m2, gammaInADMMStep1)
-        eng.load_dncnn(weights)
+        if weights is not None:
+            eng.load_dncnn(weights)
         eng.set_ssim(ssim if x_true is not None else "none")
         import torch
         t0 = time.perf_counter()

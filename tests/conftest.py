@@ -54,6 +54,11 @@ def g_loops():
 
 
 @pytest.fixture(scope="session")
+def g_tv():
+    return load_golden("tv.npz")
+
+
+@pytest.fixture(scope="session")
 def g_long():
     p = os.path.join(GOLDEN, "long.npz")
     if not os.path.exists(p):

@@ -189,6 +189,24 @@ LONG_CASES = [
 ]
 
 
+# TV baselines (iteration.py:88-99,133-140): no denoiser, colour only (operators.py:122-123 hard-code three channels).
+# Step sizes of ideas/param_memo.py:21-26 (comparisonA-4: gamma1 = 0.1, gamma2 = 0.99).
+TV_CASES = [
+    dict(tag="TV_A_blur_c", method="A-PDS-TV", deg_op="blur", ch=3, hw=(32, 48), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=0.1, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=40),
+    dict(tag="TV_A_rs_c", method="A-PDS-TV", deg_op="random_sampling", ch=3, hw=(40, 32), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=0.1, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=0.8, iters=40),
+    dict(tag="TV_FBS_blur_c", method="A-FBS-TV", deg_op="blur", ch=3, hw=(32, 32), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=0.1, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=40),
+    dict(tag="TV_B3_rs_c", method="comparisonB-3", deg_op="random_sampling", ch=3, hw=(32, 32), gaussian_nl=0.01, sp_nl=0.1,
+         gamma1=0.1, gamma2=0.49, alpha_n=0.9, alpha_s=0.9, r=0.8, iters=40),
+    dict(tag="TV_B3_blur_c", method="comparisonB-3", deg_op="blur", ch=3, hw=(32, 40), gaussian_nl=0.01, sp_nl=0.1,
+         gamma1=0.1, gamma2=0.49, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=40),
+    dict(tag="LONG_TV_A_blur_c", method="A-PDS-TV", deg_op="blur", ch=3, hw=(48, 48), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=0.1, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=1200),
+]
+
+
 def run_case(ref, case, snapshots):
     """Mirrors main.test_all_images main.py:41-69 (observation synthesis, call into test_iter)."""
     op, un = ref.operators, ref.utils_noise
@@ -247,7 +265,7 @@ def main():
     ref = ref_harness.load()
     import torch
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["assets", "ops", "noise", "denoiser", "loops"]
+    todo = a.only.split(",") if a.only else ["assets", "ops", "noise", "denoiser", "loops", "tv"]
     if "assets" in todo:
         gen_assets(ref)
     if "ops" in todo:
@@ -258,6 +276,8 @@ def main():
         gen_denoiser(ref)
     if "loops" in todo:
         gen_loops(ref, LOOP_CASES, "loops.npz", snapshots=(1, 2, 10))
+    if "tv" in todo:
+        gen_loops(ref, TV_CASES, "tv.npz", snapshots=(1, 2, 10))
     if a.long or "long" in todo:
         gen_loops(ref, LONG_CASES, "long.npz", snapshots=())
 

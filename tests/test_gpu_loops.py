@@ -172,3 +172,39 @@ def test_full_size_against_oracle_few_iterations(assets, shape, deg_op, method):
     assert rel_l2(res["x"][0], xr) < REL_L2_GATE
     assert np.max(np.abs(res["psnr"][:, 0] - psnr)) < DPSNR_GATE
     assert np.max(np.abs(res["s"][0] + 0.5 - s05)) < 1e-4
+
+
+TV_TAGS = ["TV_A_blur_c", "TV_A_rs_c", "TV_FBS_blur_c", "TV_B3_rs_c", "TV_B3_blur_c"]
+
+
+@pytest.mark.parametrize("tag", TV_TAGS)
+def test_tv_baselines(g_tv, assets, tag):
+    """A-PDS-TV / A-FBS-TV / comparisonB-3 (iteration.py:88-99,133-140) resident on the GPU against the reference's float64
+    runs: snapshots at 1 / 2 / 10 / 40 iterations, c[i] and PSNR traces."""
+    case, _ = _run(g_tv, assets, tag, 1, "tcgen05")
+    for n in (1, 2, 10, case["iters"]):
+        _, res = _run(g_tv, assets, tag, n, "tcgen05")
+        e = rel_l2(res["x"][0], g_tv[f"{tag}/x_{n}"])
+        print(f"{tag} n={n}: rel_l2(x)={e:.2e}")
+        assert e < REL_L2_GATE, (tag, n)
+        assert np.max(np.abs(res["s"][0] + 0.5 - g_tv[f"{tag}/s05_{n}"])) < 1e-4, (tag, n)
+    assert np.allclose(res["c"][:, 0], g_tv[f"{tag}/c"], rtol=5e-3, atol=2e-6), tag
+    assert np.max(np.abs(res["psnr"][:, 0] - g_tv[f"{tag}/psnr"])) < DPSNR_GATE, tag
+
+
+def test_tv_long_run(g_tv, assets):
+    """A-PDS-TV, blur, 3x48x48, 1200 iterations (param_memo.py:21-26 step sizes): the north-star gates."""
+    tag = "LONG_TV_A_blur_c"
+    case, res = _run(g_tv, assets, tag, 1200, "tcgen05")
+    e = rel_l2(res["x"][0], g_tv[f"{tag}/x_1200"])
+    dpsnr = abs(res["psnr"][-1, 0] - g_tv[f"{tag}/psnr"][-1])
+    print(f"{tag}: rel_l2={e:.2e} dPSNR={dpsnr:.2e} dB c_last={res['c'][-1, 0]:.2e}")
+    assert e < REL_L2_GATE and dpsnr < DPSNR_GATE
+
+
+def test_tv_needs_colour(assets):
+    from pnp_pds_b200 import iteration, operators
+    phi, adj = operators.get_observation_operators("Id", assets["blur_1"], 1.0)
+    x = np.full((1, 8, 8), 0.5, dtype=np.float32)
+    with pytest.raises(ValueError):
+        iteration.run_batch(x, x, x, phi, adj, dict(gamma1=0.1, gamma2=0.99), None, 1, "A-PDS-TV", 1)

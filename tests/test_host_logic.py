@@ -196,7 +196,11 @@ def test_gather_rows_gloo_world_size_2(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_GLOO_WORKER.format(root=ROOT))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", CUDA_VISIBLE_DEVICES="")
+    import socket
+    with socket.socket() as sk:                      # a free rendezvous port (a fixed one may linger in TIME_WAIT between runs)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                        "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=240)
+                        "--master-port", str(port), str(script)], env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
