@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Copies the judged evidence from gpurun_out/ (scratch) into profiles/ (tracked): bench JSON lines, the ncu launch list,
+per-kernel summaries extracted from the ncu --set full reports, and ncu_traffic.json (DRAM bytes per launch of the body-layer
+kernel, which bench.py reports as roofline.traffic).  Usage: python tools/make_profiles.py r01"""
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT, SRC = os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out")
+KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second", "launch__grid_size", "launch__block_size",
+        "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__cluster_size",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes.sum.per_second", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+
+
+def raw_page(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    return hdr, units, rows[2:]
+
+
+def summarize(rep, tag, out_name):
+    hdr, units, rows = raw_page(rep)
+    seen, out = {}, []
+    for r in rows:
+        d = dict(zip(hdr, r))
+        name = d["Kernel Name"]
+        short = name.split("(")[0].split("::")[-1]
+        if short in seen:
+            continue
+        seen[short] = 1
+        rec = {"kernel": name[:160]}
+        for k in hdr:
+            kk = k.split("TriageCompute.")[-1]
+            if kk in KEEP or ("warps_issue_stalled" in kk and kk.endswith("per_issue_active.ratio")):
+                try:
+                    v = float(d[k])
+                except ValueError:
+                    continue
+                if "stalled" in kk and v < 0.2:
+                    continue
+                rec[kk + (" [" + units[hdr.index(k)] + "]" if units[hdr.index(k)] else "")] = v
+        out.append(rec)
+    json.dump(out, open(os.path.join(OUT, f"{tag}_{out_name}"), "w"), indent=1)
+    return out
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs(OUT, exist_ok=True)
+    for name in ("default", "cfg1", "cfg2", "cfg3", "cfg2b"):
+        p = os.path.join(SRC, f"BENCH_{name}.json")
+        if os.path.exists(p):
+            shutil.copy(p, os.path.join(OUT, f"{tag}_bench_{name}.json"))
+    if os.path.exists(os.path.join(SRC, "BENCH_ref.json")):
+        shutil.copy(os.path.join(SRC, "BENCH_ref.json"), os.path.join(OUT, f"{tag}_bench_reference_arm.json"))
+    for n in (2, 4, 8):
+        p = os.path.join(SRC, f"SCALE_{n}.json")
+        if os.path.exists(p):
+            lines = [l for l in open(p).read().splitlines() if l.startswith("{")]
+            if lines:
+                open(os.path.join(OUT, f"{tag}_bench_cfg4_{n}gpu.json"), "w").write(lines[-1] + "\n")
+    if os.path.exists(os.path.join(SRC, "launches.csv")):
+        shutil.copy(os.path.join(SRC, "launches.csv"), os.path.join(OUT, f"{tag}_launches_cfg4_b8.csv"))
+    rep = os.path.join(SRC, "prof_conv_layers.ncu-rep")
+    if os.path.exists(rep):
+        recs = summarize(rep, tag, "ncu_conv_layers.json")
+        for r in recs:
+            if "conv_roll_kernel" in r["kernel"]:
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e-3, "ms": 1.0, "ns": 1e-6, "s": 1e3}
+
+                def val(prefix):
+                    k = [k for k in r if k.startswith(prefix + " [")][0]
+                    return r[k] * scale[k.split("[")[1].rstrip("]")]
+                rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+                px = 8 * 1024 * 1024
+                json.dump({"kernel": "roll::conv_roll_kernel (row-streaming body layer), cfg4 shape, 8 images (8,388,608 px) per launch",
+                           "source": f"ncu --set full --clock-control none (profiles/{tag}_ncu_conv_layers.json)",
+                           "dram_bytes_read_per_launch": rd, "dram_bytes_write_per_launch": wr, "px_per_launch": px,
+                           "bytes_per_px": (rd + wr) / px, "gpu_time_ms": val("gpu__time_duration.sum")},
+                          open(os.path.join(OUT, "ncu_traffic.json"), "w"), indent=1)
+    rep = os.path.join(SRC, "prof_pointwise.ncu-rep")
+    if os.path.exists(rep):
+        summarize(rep, tag, "ncu_pointwise.json")
+    print(sorted(os.listdir(OUT)))
+
+
+if __name__ == "__main__":
+    main()
