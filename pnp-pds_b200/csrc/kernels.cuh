@@ -66,6 +66,8 @@ struct BlurTaps {            // device arrays, built by pds_set_blur_kernel
   const short2* off[2];      // (dy, dx) per tap: out[i,j] += w * in[i+dy, j+dx] (periodic)
   int ntaps;
   int ry, rx;                // max |dy|, max |dx|
+  const float* w_host;       // host copies (owned by the handle): the register-tiled stencil takes the weight box by value
+  const short2* off_host[2];
 };
 cudaError_t launch_blur_apply(const Dims& d, const BlurTaps& taps, int adjoint, const float* in, float* out, cudaStream_t st);
 cudaError_t launch_primal_blur(const StepArgs& a, const BlurTaps& taps, cudaStream_t st);

@@ -54,6 +54,8 @@ struct pds_handle_s {
   bool ssim_now = false;
   // blur
   BlurTaps taps{};
+  std::vector<float> blur_w_host;
+  std::vector<short2> blur_off_host[2];
   bool have_blur = false;
   // denoiser
   bool have_net = false;
@@ -630,6 +632,12 @@ int pds_set_blur_kernel(pds_handle_t h, const double* k, int l) {
     h->taps.w[q] = dw;
     h->taps.off[q] = dof;
   }
+  h->blur_w_host = w;
+  h->blur_off_host[0] = off[0];
+  h->blur_off_host[1] = off[1];
+  h->taps.w_host = h->blur_w_host.data();
+  h->taps.off_host[0] = h->blur_off_host[0].data();
+  h->taps.off_host[1] = h->blur_off_host[1].data();
   h->taps.ntaps = (int)w.size();
   h->taps.ry = ry;
   h->taps.rx = rx;

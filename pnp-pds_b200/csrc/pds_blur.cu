@@ -29,6 +29,7 @@ struct BlurArgs {
   const short2* tap_off;
   int ntaps, ry, rx;
   int tiles_x;
+  float wbox[19 * 19];   // register-tiled variant: dense weight box of the launch's direction
 };
 
 __device__ __forceinline__ int wrap(int v, int n) {
@@ -133,30 +134,20 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(BlurArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Register-tiled variant (used when the tap bounding box fits RY x RX): one thread = 8 consecutive
-// output columns of one row; lane <-> row, warp <-> column octet.  Per halo row the thread loads its
-// (8 + 2 RX)-wide window with LDS.128 (pitch = 4 mod 32 floats: conflict-free) and the weight row by
-// broadcast, and applies up to (2 RX + 1) x 8 FMAs; all-zero taps are skipped by a warp-uniform branch.
-// ~7 FMAs per shared-memory load instead of 1, so the stencil runs at the FP32 pipe instead of the LSU.
-template <int V>
-__device__ __forceinline__ void ldv(const float* p, float (&r)[8]) {
-  if constexpr (V == 4) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
-  }
-}
-
+// Register-tiled variant (used when the tap bounding box fits RY x RX): one thread = OX = 16 consecutive output columns of
+// one row; lane <-> row, warp <-> column group of a 128 x 32 tile.  Per halo row the thread loads its (16 + 2 RX)-wide
+// window with LDS.128 (pitch = 4 mod 32 floats: conflict-free) and applies up to (2 RX + 1) x 16 FMAs whose weight operand
+// comes straight from the kernel-parameter constant bank (no load, no register); all-zero taps are skipped by a uniform
+// branch on that constant.  24 FMAs per shared-memory load instruction: the stencil runs on the FP32 pipe, not on the LSU.
 template <int MODE, int METHOD, int RY, int RX>
-__global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
-  constexpr int TWR = 64, THR = 32;
+__global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__ BlurArgs a) {
+  constexpr int OX = 16, TWR = 8 * OX, THR = 32;
   constexpr int HC = TWR + 2 * RX, HR = THR + 2 * RY;
   constexpr int PITCH = ((HC + 27) / 32) * 32 + 4;
-  constexpr int WROW = ((2 * RX + 1 + 3) / 4) * 4;
-  constexpr int NV = 8 + 2 * RX, NV4 = (NV + 3) / 4;
-  static_assert(8 * 7 + NV4 * 4 <= PITCH, "window read stays inside the padded row");
+  constexpr int NV = OX + 2 * RX, NV4 = (NV + 3) / 4;
+  static_assert(OX * 7 + NV4 * 4 <= PITCH, "window read stays inside the padded row");
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                       // [HR][PITCH]
-  float* wbox = smem + HR * PITCH;          // [2RY+1][WROW]
   __shared__ double red[NACC * 8];
   const Dims d = a.s.d;
   const int plane = blockIdx.y;
@@ -165,10 +156,18 @@ __global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
   const int x0 = txi * TWR, y0 = tyi * THR;
   const size_t pbase = (size_t)plane * d.hw;
 
-  for (int k = threadIdx.x; k < (2 * RY + 1) * WROW; k += 256) wbox[k] = 0.f;
+  // stage the halo tile; the periodic wrap is one conditional add / subtract when the image is at least as large as the
+  // halo reach (always, except for toy sizes)
+  const bool easy = d.H >= RY + THR && d.W >= RX + TWR;
   for (int idx = threadIdx.x; idx < HR * HC; idx += 256) {
     const int hy = idx / HC, hx = idx - hy * HC;
-    const int gy = wrap(y0 - RY + hy, d.H), gx = wrap(x0 - RX + hx, d.W);
+    int gy = y0 - RY + hy, gx = x0 - RX + hx;
+    if (easy) {
+      gy += gy < 0 ? d.H : 0; gy -= gy >= d.H ? d.H : 0;
+      gx += gx < 0 ? d.W : 0; gx -= gx >= d.W ? d.W : 0;
+    } else {
+      gy = wrap(gy, d.H); gx = wrap(gx, d.W);
+    }
     const size_t g = pbase + (size_t)gy * d.W + gx;
     float v;
     if constexpr (MODE == kApply) v = __ldg(a.in + g);
@@ -177,32 +176,26 @@ __global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
     tile[hy * PITCH + hx] = v;
   }
   __syncthreads();
-  for (int k = threadIdx.x; k < a.ntaps; k += 256) {
-    const short2 o = a.tap_off[k];
-    wbox[((int)o.x + RY) * WROW + (int)o.y + RX] = a.tap_w[k];
-  }
-  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float acc[8];
+  float acc[OX];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+  for (int c = 0; c < OX; ++c) acc[c] = 0.f;
 #pragma unroll
   for (int dyi = 0; dyi < 2 * RY + 1; ++dyi) {
-    const float4* rp = reinterpret_cast<const float4*>(tile + (lane + dyi) * PITCH + 8 * warp);
+    const float4* rp = reinterpret_cast<const float4*>(tile + (lane + dyi) * PITCH + OX * warp);
     float v[NV4 * 4];
 #pragma unroll
     for (int j = 0; j < NV4; ++j) {
       const float4 q = rp[j];
       v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
     }
-    const float* wr = wbox + dyi * WROW;
 #pragma unroll
     for (int dxi = 0; dxi < 2 * RX + 1; ++dxi) {
-      const float w = wr[dxi];
-      if (w != 0.f) {                       // warp-uniform: the weight does not depend on the thread
+      const float w = a.wbox[dyi * (2 * RX + 1) + dxi];      // constant-bank operand
+      if (w != 0.f) {                       // uniform: the weight does not depend on the thread
 #pragma unroll
-        for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, v[c + dxi], acc[c]);
+        for (int c = 0; c < OX; ++c) acc[c] = fmaf(w, v[c + dxi], acc[c]);
       }
     }
   }
@@ -216,73 +209,77 @@ __global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
     la = p.lam * p.alpha;
     lg4 = 4.f * p.lam * p.g2;
   }
-  const int gy = y0 + lane, gx0 = x0 + 8 * warp;
+  const int gy = y0 + lane, gx0 = x0 + OX * warp;
   if (gy < d.H && gx0 < d.W) {
     const size_t g0 = pbase + (size_t)gy * d.W + gx0;
     const bool vec = ((d.W & 3) == 0);       // rows start 16-byte aligned and a float4 is never split by the edge
-    const int nvalid = (d.W - gx0) < 8 ? (d.W - gx0) : 8;
-    float res[8], xv[8], xnv[8], tv[8], ob[8], sn[8], so[8], xt[8];
-    auto load8 = [&](const float* base, float (&r)[8]) {
+    const int nvalid = (d.W - gx0) < OX ? (d.W - gx0) : OX;
+    // four outputs at a time (keeps the live registers of the pointwise tail small: occupancy matters for the staging loads)
+    auto load4 = [&](const float* base, int q, float (&r)[4]) {
       if (vec) {
-        const float4 q0 = __ldg(reinterpret_cast<const float4*>(base + g0));
-        r[0] = q0.x; r[1] = q0.y; r[2] = q0.z; r[3] = q0.w;
-        if (nvalid > 4) {
-          const float4 q1 = __ldg(reinterpret_cast<const float4*>(base + g0) + 1);
-          r[4] = q1.x; r[5] = q1.y; r[6] = q1.z; r[7] = q1.w;
-        }
+        const float4 t = __ldg(reinterpret_cast<const float4*>(base + g0) + q);
+        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
       } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) if (c < nvalid) r[c] = __ldg(base + g0 + c);
+        for (int c = 0; c < 4; ++c) r[c] = (4 * q + c < nvalid) ? __ldg(base + g0 + 4 * q + c) : 0.f;
       }
     };
-    auto store8 = [&](float* base, const float (&r)[8]) {
+    auto store4 = [&](float* base, int q, const float (&r)[4]) {
       if (vec) {
-        *reinterpret_cast<float4*>(base + g0) = make_float4(r[0], r[1], r[2], r[3]);
-        if (nvalid > 4) *(reinterpret_cast<float4*>(base + g0) + 1) = make_float4(r[4], r[5], r[6], r[7]);
+        *(reinterpret_cast<float4*>(base + g0) + q) = make_float4(r[0], r[1], r[2], r[3]);
       } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) if (c < nvalid) base[g0 + c] = r[c];
+        for (int c = 0; c < 4; ++c) if (4 * q + c < nvalid) base[g0 + 4 * q + c] = r[c];
       }
     };
-    if constexpr (MODE == kApply) {
-      store8(a.out, acc);
-    } else if constexpr (MODE == kPrimal) {
-      load8(a.s.x, xv);
+    const bool have_true = MODE == kDual && a.s.xtrue != nullptr;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) res[c] = fmaf(-p.g1 * sg, acc[c], xv[c]);
-      store8(a.s.u, res);
-    } else {
-      load8(a.s.xn, xnv);
-      load8(a.s.x, xv);
-      load8(a.s.t, tv);                      // same thread reads then writes its own elements
-      load8(a.s.obs, ob);
-      if constexpr (METHOD == PDS_METHOD_B) {
-        load8(a.s.s_new, sn);
-        load8(a.s.s_old, so);
-      }
-      const bool have_true = a.s.xtrue != nullptr;
-      if (have_true) load8(a.s.xtrue, xt);
+    for (int q = 0; q < OX / 4; ++q) {
+      if (4 * q >= nvalid) break;
+      float r[4] = {acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]};
+      if constexpr (MODE == kApply) {
+        store4(a.out, q, r);
+      } else if constexpr (MODE == kPrimal) {
+        float xv[4];
+        load4(a.s.x, q, xv);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        if (c >= nvalid) continue;
-        float v = acc[c];
-        if constexpr (METHOD == PDS_METHOD_B) v += 2.f * sn[c] - so[c];
-        const float w = fmaf(p.g2, v, sg * tv[c]);
-        if constexpr (METHOD == PDS_METHOD_C) {
-          res[c] = gkl_dual(w, ob[c], la, lg4);
-        } else {
-          res[c] = fmaf(-p.g2, ob[c], w);
-          acc_t = fmaf(res[c], res[c], acc_t);
+        for (int c = 0; c < 4; ++c) r[c] = fmaf(-p.g1 * sg, r[c], xv[c]);
+        store4(a.s.u, q, r);
+      } else {
+        float xv[4], xnv[4], tv[4], ob[4];
+        load4(a.s.xn, q, xnv);
+        load4(a.s.x, q, xv);
+        load4(a.s.t, q, tv);                 // same thread reads then writes its own elements
+        load4(a.s.obs, q, ob);
+        if constexpr (METHOD == PDS_METHOD_B) {
+          float sn[4], so[4];
+          load4(a.s.s_new, q, sn);
+          load4(a.s.s_old, q, so);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) r[c] += 2.f * sn[c] - so[c];
         }
-        const float dx = xnv[c] - xv[c];
-        acc_dx = fmaf(dx, dx, acc_dx);
-        acc_x = fmaf(xv[c], xv[c], acc_x);
-        if (have_true) {
-          const float e = xnv[c] - xt[c];
-          acc_e = fmaf(e, e, acc_e);
+        float xt[4] = {0.f, 0.f, 0.f, 0.f};
+        if (have_true) load4(a.s.xtrue, q, xt);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (4 * q + c >= nvalid) continue;
+          const float w = fmaf(p.g2, r[c], sg * tv[c]);
+          if constexpr (METHOD == PDS_METHOD_C) {
+            tv[c] = gkl_dual(w, ob[c], la, lg4);
+          } else {
+            tv[c] = fmaf(-p.g2, ob[c], w);
+            acc_t = fmaf(tv[c], tv[c], acc_t);
+          }
+          const float dx = xnv[c] - xv[c];
+          acc_dx = fmaf(dx, dx, acc_dx);
+          acc_x = fmaf(xv[c], xv[c], acc_x);
+          if (have_true) {
+            const float e = xnv[c] - xt[c];
+            acc_e = fmaf(e, e, acc_e);
+          }
         }
+        store4(a.s.t, q, tv);
       }
-      store8(a.s.t, res);
     }
   }
   if constexpr (MODE == kDual) {
@@ -293,8 +290,8 @@ __global__ void __launch_bounds__(256) blur_rt_kernel(BlurArgs a) {
 
 template <int RY, int RX>
 constexpr size_t rt_smem_bytes() {
-  constexpr int HC = 64 + 2 * RX, HR = 32 + 2 * RY, PITCH = ((HC + 27) / 32) * 32 + 4, WROW = ((2 * RX + 1 + 3) / 4) * 4;
-  return (size_t)(HR * PITCH + (2 * RY + 1) * WROW) * sizeof(float);
+  constexpr int HC = 128 + 2 * RX, HR = 32 + 2 * RY, PITCH = ((HC + 27) / 32) * 32 + 4;
+  return (size_t)(HR * PITCH) * sizeof(float);
 }
 
 template <int MODE, int METHOD, int RY, int RX>
@@ -304,9 +301,19 @@ cudaError_t launch_rt(BlurArgs& a, const Dims& d, const BlurTaps& t, int which, 
   a.ntaps = t.ntaps;
   a.ry = t.ry;
   a.rx = t.rx;
-  a.tiles_x = (d.W + 63) / 64;
+  // dense weight box [dy + RY][dx + RX] of this direction, handed over by value (constant bank)
+  for (int i = 0; i < (2 * RY + 1) * (2 * RX + 1); ++i) a.wbox[i] = 0.f;
+  for (int k = 0; k < t.ntaps; ++k)
+    a.wbox[((int)t.off_host[which][k].x + RY) * (2 * RX + 1) + (int)t.off_host[which][k].y + RX] = t.w_host[k];
+  a.tiles_x = (d.W + 127) / 128;
   const int tiles_y = (d.H + 31) / 32;
   dim3 grid(a.tiles_x * tiles_y, d.B * d.C);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(blur_rt_kernel<MODE, METHOD, RY, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_smem_bytes<RY, RX>());
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
   blur_rt_kernel<MODE, METHOD, RY, RX><<<grid, 256, rt_smem_bytes<RY, RX>(), st>>>(a);
   return cudaGetLastError();
 }
