@@ -139,8 +139,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
         if (elect_one()) {
           mbar_expect_tx(bFull + 8 * slot, kPlaneBytes);
-          if (a.variant & 4) tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, -1, -1, p);   // perf experiment: L2-resident loads
-          else tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
+          tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
         }
         __syncwarp();
       }
@@ -162,10 +161,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tc_fence_after();
         const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
         if (elect_one()) {
-          if (!(a.variant & 8)) {                       // perf experiment: bit 3 skips the MMAs
-            if (p == 0) issue_plane<NW, true>(d_tmem, a_lo, w_lo);
-            else issue_plane<NW, false>(d_tmem, a_lo, w_lo);
-          }
+          if (p == 0) issue_plane<NW, true>(d_tmem, a_lo, w_lo);
+          else issue_plane<NW, false>(d_tmem, a_lo, w_lo);
           umma_commit(bEmpty + 8 * slot);              // slot may be overwritten once these MMAs retire
           if (p == 1) umma_commit(bTFull + 8 * acc);   // accumulator complete
         }
@@ -195,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
-      if (y < a.H && x < a.W && !(a.variant & 2)) {     // perf experiment: bit 1 skips the stores
+      if (y < a.H && x < a.W) {
         const size_t pix = (size_t)y * a.W + x;
         __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
         uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
@@ -975,17 +972,16 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-static void fill_common(TcArgs& a, TcPlan* plan, int nimg, int variant) {
+static void fill_common(TcArgs& a, TcPlan* plan, int nimg) {
   a.H = plan->H;
   a.W = plan->W;
   a.nimg = nimg;
   a.tiles_x = (plan->W + kTileCols - 1) / kTileCols;
   a.tiles_y = (plan->H + kTileRows - 1) / kTileRows;
   a.ntiles = a.tiles_x * a.tiles_y * nimg;
-  a.variant = variant;
 }
 
-cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st) {
+cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st) {
   TcArgs a{};
   a.w_img = L.w_mid_tc;
   a.bias = L.bias;
@@ -993,12 +989,12 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   a.slope = slope;
   a.lo_scale = L.lo_scale;
   a.C = 64;
-  fill_common(a, plan, nimg, variant);
+  fill_common(a, plan, nimg);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
   return launch_pdl(conv_tc_kernel<64>, grid, kThreads, Geo<64>::kSmemBytes, st, plan->map[in_buf], a);
 }
 
-cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st) {
+cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st) {
   TcArgs a{};
   a.w_img = L.w_mid_tc2;
   a.bias = L.bias;
@@ -1006,7 +1002,7 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
   a.slope = slope;
   a.lo_scale = L.lo_scale;
   a.C = 64;
-  fill_common(a, plan, nimg, variant);
+  fill_common(a, plan, nimg);
   const int npairs = (a.ntiles + 1) / 2;
   const int nclusters = npairs < plan->num_sms / 2 ? npairs : plan->num_sms / 2;
   return launch_pdl(two::conv_tc2_kernel, 2 * nclusters, kThreads, two::kSmemBytes2, st, plan->map[in_buf], a);
@@ -1035,7 +1031,7 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
 }
 
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in, float residual_sign,
-                                int clamp, float* out, int variant, cudaStream_t st) {
+                                int clamp, float* out, cudaStream_t st) {
   TcArgs a{};
   a.w_img = L.w_last_tc;
   a.bias = L.bias;
@@ -1045,7 +1041,7 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
   a.res_sign = residual_sign;
   a.clamp = clamp;
   a.lo_scale = L.lo_scale;
-  fill_common(a, plan, nimg, 0);
+  fill_common(a, plan, nimg);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
   if (C == 1) return launch_pdl(last::conv_last_tc_kernel<1>, grid, kThreads, last::kSmemBytesL, st, plan->map[in_buf], a);
   if (C == 3) return launch_pdl(last::conv_last_tc_kernel<3>, grid, kThreads, last::kSmemBytesL, st, plan->map[in_buf], a);

@@ -115,12 +115,12 @@ struct TcPlan;  // opaque: tensor maps for the two activation buffers
 int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** out);  // returns 0 / error (message set)
 void tc_plan_destroy(TcPlan* p);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
-cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
+cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
                                  cudaStream_t st);
-cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, int variant, cudaStream_t st);
+cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
-                                float residual_sign, int clamp, float* out, int variant, cudaStream_t st);
+                                float residual_sign, int clamp, float* out, cudaStream_t st);
 int tc_num_sms();
 // row-streaming body layer (dncnn_roll.cu): band height for a launch of nimg images (0 = not applicable, use the tile kernels)
 int roll_setup();

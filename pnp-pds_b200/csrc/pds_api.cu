@@ -218,16 +218,16 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
       if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && band > 0) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {
-        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
-        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, h->tc_variant, st));
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, st));
       } else {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_simt(nimg, d.H, d.W, h->act[src], h->layers[l], h->slope, h->act[src ^ 1], st));
       }
       src ^= 1;
     }
     if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
-      PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last_tc(h->tc, src, nimg, d.C, h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, h->tc_variant, st));
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last_tc(h->tc, src, nimg, d.C, h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
     }
@@ -564,7 +564,7 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   pds_handle_s* h = new (std::nothrow) pds_handle_s();
   PDS_REQUIRE(h, "out of host memory");
   h->cfg = *cfg;
-  if (const char* v = std::getenv("PDS_TC_VARIANT")) h->tc_variant = std::atoi(v);   // perf-experiment switches (dncnn_tc.cu)
+  if (const char* v = std::getenv("PDS_TC_VARIANT")) h->tc_variant = std::atoi(v);   // kernel-selection switches (run_dncnn)
   h->d = Dims{cfg->batch, cfg->channels, cfg->height, cfg->width, cfg->height * cfg->width,
               cfg->channels * cfg->height * cfg->width};
   const size_t n = total_elems(h);

@@ -34,7 +34,6 @@ struct TcArgs {
   float slope;
   float lo_scale;         // 2^-S of this layer's e4m3 correction accumulator
   int H, W, nimg, tiles_x, tiles_y, ntiles;
-  int variant;
   // last layer only
   const float* net_in;    // (nimg, C, H, W) network input (residual)
   float* out_f32;         // (nimg, C, H, W)

@@ -129,3 +129,23 @@ def test_row_streaming_body_kernel_matches_tile_kernels(shape):
     for b in (0, B - 1):
         ref = O.dncnn_forward(w.layers, x[b], w.slope, w.residual_sign, w.clamp)
         assert float(np.max(np.abs(outs["roll"][b] - ref))) < TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 48, 24), (3, 3, 50, 37), (2, 1, 130, 70)])
+def test_tile_kernels_one_and_two_cta_agree(shape):
+    """The 1-CTA and the CTA-pair tile kernels issue the same MMAs in the same order: bit-identical outputs, including an
+    odd tile count (the pair's second tile is a dead duplicate) and ragged edges."""
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    B, C, H, W = shape
+    w = load_weights(weights_path(SIMPLE[1] if C == 3 else SIMPLE[0]))
+    x = np.random.default_rng(21).random(shape).astype(np.float32)
+    outs = []
+    for variant in (16, 32):                       # force the 1-CTA / the 2-CTA tile kernel for the body layers
+        with Engine(B, C, H, W, conv_engine="tcgen05") as e:
+            e.load_dncnn(w)
+            e.set_tc_variant(variant)
+            outs.append(e.dncnn_forward(e.to_device(x)).cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    ref = O.dncnn_forward(w.layers, x[0], w.slope, w.residual_sign, w.clamp)
+    assert float(np.max(np.abs(outs[0][0] - ref))) < TOL
