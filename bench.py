@@ -388,8 +388,8 @@ def main():
         # which body-layer kernel the library dispatches for this launch shape (pds_api.cu run_dncnn)
         if a.engine != "tcgen05":
             mid_kernel = "conv_mid_simt_kernel"
-        elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W) > 0:
-            mid_kernel = "roll::conv_roll_kernel (row-streaming cta_group::2 body layer, %d-row bands)" % eng.lib.pds_debug_roll_band_rows(int(chunk), H, W)
+        elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0) > 0:
+            mid_kernel = "roll::conv_roll_kernel (row-streaming cta_group::2 body layer, %d-row bands)" % eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0)
         elif chunk * ((H + 15) // 16) * ((W + 7) // 8) >= 4096:
             mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
         else:

@@ -164,12 +164,12 @@ long long pds_kernel_launches(pds_handle_t h);
 size_t pds_workspace_bytes(pds_handle_t h);
 
 /* ---- test hooks (hardware probes used by tests/test_gpu_tcgen05.py; not part of the drop-in surface) ---- */
-/* perf-experiment switches of the tcgen05 engine: bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel for the body layers,
- * bit 7 disables the row-streaming body kernel (dncnn_roll.cu) */
+/* kernel-selection switches of the tcgen05 engine: bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel for the body layers,
+ * bit 6 forces the row-streaming body kernel (dncnn_roll.cu) wherever the width is a multiple of 128, bit 7 disables it */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant);
 /* rows per band the row-streaming body kernel would use for a launch of nimg images of H x W on the current device;
- * 0 = the tile kernels run instead (width not a multiple of 128, or too few bands for the CTA pairs) */
-int pds_debug_roll_band_rows(int nimg, int H, int W);
+ * 0 = the tile kernels run instead (width not a multiple of 128, or the cost model prefers tiles; force != 0 skips that comparison) */
+int pds_debug_roll_band_rows(int nimg, int H, int W, int force);
 /* one tcgen05.mma (M=128, N=16, K=16, B = identity) over a shared-memory region whose 16-byte chunk c
  * holds (c & 1023, c >> 10) repeated; out_host[128][16] therefore reveals which chunk fed every (row, k) */
 int pds_debug_umma_probe(unsigned a_off, unsigned sbo, unsigned base_off, unsigned region_bytes, float* out_host);

@@ -63,7 +63,7 @@ def _declare(lib):
         "pds_kernel_launches": (C.c_longlong, [vp]),
         "pds_workspace_bytes": (sz, [vp]),
         "pds_debug_set_tc_variant": (i, [vp, i]),
-        "pds_debug_roll_band_rows": (i, [i, i, i]),
+        "pds_debug_roll_band_rows": (i, [i, i, i, i]),
         "pds_debug_umma_probe": (i, [u, u, u, u, vp]),
         "pds_debug_tma_probe": (i, [vp, i, i, i, i, i, i, vp]),
     }

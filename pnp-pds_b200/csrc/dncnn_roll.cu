@@ -249,16 +249,28 @@ int roll_setup() {
   return 0;
 }
 
-// Rows per band: as tall as possible (the two extra input rows per band are the only overhead) while every CTA pair
-// still gets several bands; 0 = the launch is too small or the width does not split into 128-pixel strips.
-int roll_band_rows(int nimg, int H, int W, int num_sms) {
-  if (W % roll::kStripW != 0 || H < 16) return 0;
+// Rows per band, or 0 when the tile kernels are the better choice for this launch.  Cost model in units of "one 128-pixel row
+// step of a CTA pair": a band of rb rows costs rb + 2 steps (two halo rows), the launch costs ceil(units / pairs) bands per
+// pair; the 2-CTA tile kernel needs ~1.12 steps per tile pair (it re-reads the A operand, ncu: 3246 vs 2912 cycles).
+// `force`: ignore the comparison with the tile kernels (tests).
+int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
+  if (W % roll::kStripW != 0 || H < 8 || nimg < 1) return 0;
   const long long npx = (W + 2 * roll::kStripW - 1) / (2 * roll::kStripW);
-  const long long clusters = num_sms / 2;
-  int rb = 64;
-  while (rb > 16 && (long long)nimg * ((H + rb - 1) / rb) * npx < 4 * clusters) rb >>= 1;
-  if ((long long)nimg * ((H + rb - 1) / rb) * npx < 2 * clusters) return 0;
-  return rb;
+  const long long pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
+  long long best_cost = -1;
+  int best_rb = 0;
+  for (int rb = 8; rb <= 64; ++rb) {
+    const long long units = (long long)nimg * ((H + rb - 1) / rb) * npx;
+    const long long cost = ((units + pairs - 1) / pairs) * (rb + 2);
+    if (best_cost < 0 || cost <= best_cost) {
+      best_cost = cost;
+      best_rb = rb;
+    }
+  }
+  if (force) return best_rb;
+  const long long tile_pairs = ((long long)nimg * ((H + kTileRows - 1) / kTileRows) * ((W + kTileCols - 1) / kTileCols) + 1) / 2;
+  const double tile_cost = 1.12 * (double)((tile_pairs + pairs - 1) / pairs);
+  return (double)best_cost < tile_cost ? best_rb : 0;
 }
 
 cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, cudaStream_t st) {

@@ -124,7 +124,7 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
 int tc_num_sms();
 // row-streaming body layer (dncnn_roll.cu): band height for a launch of nimg images (0 = not applicable, use the tile kernels)
 int roll_setup();
-int roll_band_rows(int nimg, int H, int W, int num_sms);
+int roll_band_rows(int nimg, int H, int W, int num_sms, bool force);
 cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, cudaStream_t st);
 
 }  // namespace pds

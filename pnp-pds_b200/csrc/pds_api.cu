@@ -211,9 +211,10 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     for (int l = 1; l < h->depth - 1; ++l) {
       // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and the launch
       // has enough row bands for every CTA pair; else the 2-CTA tile kernel for large launches and the 1-CTA tile kernel
-      // for single small images.  PDS_TC_VARIANT bit 7 disables row streaming, bit 4 / bit 5 force 1-CTA / 2-CTA tiles.
+      // for single small images.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width allows,
+      // bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel.
       const long long ntiles = (long long)nimg * ((d.H + 15) / 16) * ((d.W + 7) / 8);
-      const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached());
+      const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
       const bool two_cta = (h->tc_variant & 32) || (!(h->tc_variant & 16) && ntiles >= 4096);
       if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && band > 0) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, st));
@@ -1004,7 +1005,7 @@ int pds_profile_read(pds_handle_t h, double* ms_out, long long* count_out, int r
 long long pds_kernel_launches(pds_handle_t h) { return h ? h->launches : -1; }
 size_t pds_workspace_bytes(pds_handle_t h) { return h ? h->bytes : 0; }
 
-int pds_debug_roll_band_rows(int nimg, int H, int W) { return pds::roll_band_rows(nimg, H, W, pds::tc_num_sms()); }
+int pds_debug_roll_band_rows(int nimg, int H, int W, int force) { return pds::roll_band_rows(nimg, H, W, pds::tc_num_sms(), force != 0); }
 
 /* test hook: perf-experiment switches of the tcgen05 engine (see run_dncnn) */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant) {
