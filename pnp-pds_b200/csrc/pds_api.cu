@@ -75,6 +75,10 @@ struct pds_handle_s {
   // optional per-kernel timing (bench.py roofline): event pairs around the launches of each category
   bool prof = false;
   std::vector<cudaEvent_t> ev_pool;
+  // pds_restore_host: x_obsrv / x_true are uploaded on a side stream while the first primal step and denoiser pass run
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_enter = nullptr, ev_inputs = nullptr;
+  bool inputs_pending = false;
   size_t ev_used = 0;
   struct ProfRec { int cat; cudaEvent_t a, b; };
   std::vector<ProfRec> prof_recs;
@@ -273,6 +277,15 @@ StepArgs step_args(pds_handle_s* h) {
   return a;
 }
 
+// The first consumer of x_obsrv / x_true after pds_restore_host waits for their side-stream upload here.
+int wait_inputs(pds_handle_s* h, cudaStream_t st) {
+  if (h->inputs_pending) {
+    PDS_CUDA_OK(cudaStreamWaitEvent(st, h->ev_inputs, 0));
+    h->inputs_pending = false;
+  }
+  return 0;
+}
+
 // One iteration of A-/B-/C-Proposed (iteration.py:48-63).
 int pds_iteration(pds_handle_s* h, cudaStream_t st) {
   StepArgs a = step_args(h);
@@ -284,6 +297,7 @@ int pds_iteration(pds_handle_s* h, cudaStream_t st) {
   if (h->cfg.method == PDS_METHOD_B)
     PDS_LAUNCH_P(h, PDS_PROF_L1BALL, st, launch_l1ball(h->d, a.s_old, h->t, h->prm, a.sums_prev, -1.f, h->sbuf[h->scur ^ 1], nullptr, st));
   PDS_TRY(run_dncnn(h, h->u, h->xbuf[h->cur ^ 1], st));
+  PDS_TRY(wait_inputs(h, st));              // x_obsrv, x_true are first read by the dual update
   // y_{k+1}
   if (blur) PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_blur(a, h->taps, st));
   else PDS_LAUNCH_P(h, PDS_PROF_DUAL, st, launch_dual_pointwise(a, st));
@@ -599,6 +613,9 @@ int pds_destroy(pds_handle_t h) {
   cudaSetDevice(h->cfg.device);
   if (h->tc) tc_plan_destroy(h->tc);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->ev_enter) cudaEventDestroy(h->ev_enter);
+  if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
   return 0;
@@ -692,6 +709,14 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
     need += (size_t)(co * ci * 9 + co) * 4;
   }
   PDS_REQUIRE(need == nbytes, "PDSW blob size mismatch");
+  {
+    // the fp16 / e4m3 operand split of the tcgen05 engine covers |w| < 2^14 (tc_split_scales); every shipped checkpoint has |w| < 4
+    const float* wv = reinterpret_cast<const float*>(p + 48);
+    const size_t nw = (nbytes - 48) / 4;
+    bool ok = true;
+    for (size_t i = 0; i < nw; ++i) ok = ok && std::isfinite(wv[i]) && std::fabs(wv[i]) < 16384.f;
+    PDS_REQUIRE(ok, "checkpoint holds non-finite or huge (>= 2^14) parameters");
+  }
   h->depth = depth;
   h->slope = fl[0];
   h->res_sign = fl[1];
@@ -885,6 +910,7 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   for (int i = 0; i < n_iter; ++i) {
     h->ssim_now = h->ssim_mode == 1 || (h->ssim_mode == 2 && i == n_iter - 1);
+    if (h->cfg.method > PDS_METHOD_C) PDS_TRY(wait_inputs(h, st));    // every other loop reads x_obsrv at its first step
     if (h->cfg.method <= PDS_METHOD_C) PDS_TRY(pds_iteration(h, st));
     else if (h->cfg.method <= PDS_METHOD_RED) PDS_TRY(fbs_red_iteration(h, st));
     else if (h->cfg.method >= PDS_METHOD_TV_A) PDS_TRY(tv_iteration(h, st));
@@ -953,16 +979,28 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nb = total_elems(h) * sizeof(float);
   h->cur = h->scur = h->iter = 0;
+  if (!h->copy_stream) {
+    PDS_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    PDS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming));
+    PDS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming));
+  }
+  // x_0 on the caller's stream (the first primal step needs it); x_obsrv and x_true on a side stream, ordered after whatever
+  // the caller's stream was still doing with those buffers, and joined by the first kernel that reads them (wait_inputs)
   PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0], x0, nb, cudaMemcpyHostToDevice, st));
-  PDS_CUDA_OK(cudaMemcpyAsync(h->obs, obs, nb, cudaMemcpyHostToDevice, st));
+  PDS_CUDA_OK(cudaEventRecord(h->ev_enter, st));        // after x_0: it gets the whole link first
+  PDS_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_enter, 0));
+  PDS_CUDA_OK(cudaMemcpyAsync(h->obs, obs, nb, cudaMemcpyHostToDevice, h->copy_stream));
   h->have_true = xtrue != nullptr;
-  if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyHostToDevice, st));
+  if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyHostToDevice, h->copy_stream));
+  PDS_CUDA_OK(cudaEventRecord(h->ev_inputs, h->copy_stream));
+  h->inputs_pending = true;
   PDS_CUDA_OK(cudaMemsetAsync(h->t, 0, nb, st));
   if (h->y1) PDS_CUDA_OK(cudaMemsetAsync(h->y1, 0, 2 * nb, st));
   if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
   h->have_problem = true;
   PDS_TRY(pds_run(h, n_iter, stream));
+  PDS_TRY(wait_inputs(h, st));              // n_iter == 0: still join the side stream before returning
   PDS_CUDA_OK(cudaMemcpyAsync(x_out, h->xbuf[h->cur], nb, cudaMemcpyDeviceToHost, st));
   if (s_out) {
     if (h->sbuf[0]) PDS_CUDA_OK(cudaMemcpyAsync(s_out, h->sbuf[h->scur], nb, cudaMemcpyDeviceToHost, st));
