@@ -178,3 +178,43 @@ def grid_search(images, grid, experimental_settings, method_common, ch, path_ker
         for k, it in enumerate(ids):
             rows[it - lo] = (res["psnr"][-1, k], res["ssim"][-1, k], res["c"][-1, k])
     return gather_rows(rows, n_items).reshape(n_img, n_grid, 3)
+
+
+def sweep_experiments():
+    """The experiment list of the reference's sweep driver (main.py:130-153): 5 noise levels x {blur, random_sampling} x
+    {A-Proposed, A-PDS-TV: alpha_n = 0.82 ... 1.00; A-PnPFBS-DnCNN, A-RED-DnCNN: myLambda = 0.2 ... 1.99}."""
+    out = []
+    for nl in (0.0025, 0.005, 0.01, 0.02, 0.04):
+        for obs in ("blur", "random_sampling"):
+            max_iter = 1200 if obs == "blur" else 3000
+            settings = {"gaussian_nl": nl, "sp_nl": 0, "poisson_noise": False, "deg_op": obs, "r": 0.8}
+            for method in ("A-Proposed", "A-PDS-TV"):
+                for i in range(10):
+                    out.append({"settings": settings, "configs": {},
+                                "method": {"method": method, "max_iter": max_iter, "gamma1": 0.125 if method == "A-PDS-TV" else 0.99,
+                                           "gamma2": 0.99, "alpha_n": 0.8 + (i + 1) * 0.02}})
+            for method in ("A-PnPFBS-DnCNN", "A-RED-DnCNN"):
+                for i in range(10):
+                    lam = (i + 1) * 0.2
+                    out.append({"settings": settings, "configs": {},
+                                "method": {"method": method, "max_iter": max_iter, "gamma1": 1, "myLambda": 1.99 if lam == 2 else lam}})
+    return out
+
+
+def main(config=None, experiments=None):
+    """main.py:125-159: run the sweep, one SUMMARY(<timestamp>).txt line per experiment (utils_textfile)."""
+    from .utils.utils_textfile import add_footer_textfile, touch_textfile, write_textfile
+    config = config or load_config()
+    filepath = os.path.join(config["path_result"], "SUMMARY(" + datetime.datetime.now().strftime("%Y%m%d %H%M%S %f") + ").txt")
+    touch_textfile(filepath)
+    data = None
+    for e in (sweep_experiments() if experiments is None else experiments):
+        data = test_all_images(e["settings"], e["method"], e["configs"], config=config)
+        write_textfile(filepath, data)
+    if data is not None:
+        add_footer_textfile(filepath, data)
+    return filepath
+
+
+if __name__ == "__main__":
+    main()

@@ -85,3 +85,25 @@ def test_grid_search_single_rank_matches_individual_runs(assets):
     one = iteration.run_batch(x0[None], obs[None], images[1][None], phi, adj, p, path, 6, "A-Proposed", 1)
     assert abs(table[1, 3, 0] - one["psnr"][-1, 0]) < 1e-9 and abs(table[1, 3, 2] - one["c"][-1, 0]) < 1e-12
     assert len({round(v, 6) for v in table[0, :, 0]}) == 4                                         # grid points differ
+
+
+def test_sweep_driver_writes_summary_file(ref_tree):
+    """main.main (main.py:125-159) over a two-experiment list: SUMMARY(<timestamp>).txt with the reference's layout, one line per
+    experiment; includes a TV baseline (no denoiser) next to ours-A."""
+    from pnp_pds_b200 import main as pmain
+    from pnp_pds_b200.utils import utils_textfile as tf
+    settings = {"gaussian_nl": 0.01, "sp_nl": 0, "poisson_noise": False, "deg_op": "blur", "r": 0.8}
+    ex = [{"settings": settings, "configs": {"ch": 3},
+           "method": {"method": "A-Proposed", "architecture": "DnCNN_nobn_nch_3_nlev_0.01", "max_iter": 3, "gamma1": 0.99, "gamma2": 0.99, "alpha_n": 0.9}},
+          {"settings": settings, "configs": {"ch": 3},
+           "method": {"method": "A-PDS-TV", "architecture": "DnCNN_nobn_nch_3_nlev_0.01", "max_iter": 3, "gamma1": 0.125, "gamma2": 0.99, "alpha_n": 0.9}}]
+    path = pmain.main(config=ref_tree, experiments=ex)
+    lines = open(path).read().split("\n")
+    assert os.path.basename(path).startswith("SUMMARY(") and lines[0] + "\n" == tf.get_csv_header()
+    assert len(lines) == 5 and lines[4] == ""                      # header, 2 experiments, footer, trailing newline
+    a, t = lines[1].split(","), lines[2].split(",")
+    assert a[0] == "blur" and a[3] == "A-Proposed" and a[4] == "PnP-PDS" and a[5] == "DnCNN"
+    assert t[3] == "A-PDS-TV" and t[4] == "PDS" and t[5] == ""
+    assert 10 < float(a[6]) < 50 and 10 < float(t[6]) < 50        # average PSNR of three images
+    assert len(a) == 17 + 4 * 3 + 1                                 # 17 columns, 4 values per image, trailing comma
+    assert lines[3] == "im0.png,im1.png,im2.png,"

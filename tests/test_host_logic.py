@@ -220,3 +220,33 @@ def test_row_streaming_band_selection_cost_model():
     assert f(1, 256, 256, 0) == 0 and f(1, 512, 512, 0) == 0     # single small images: too few bands, tiles win
     assert f(1, 100, 100, 0) == 0 and f(1, 100, 100, 1) == 0      # width not a multiple of 128: never
     assert f(1, 256, 256, 1) >= 8                         # forced (tests)
+
+
+def test_summary_textfile_matches_reference_format(tmp_path):
+    """utils_textfile against strings produced by the reference's writer (tests/golden/textfile.json, recorded here)."""
+    import json
+    from pnp_pds_b200.utils import utils_textfile as tf
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "textfile.json")))
+    data = dict(g["data"])
+    data["results"] = {int(k): v for k, v in data["results"].items()}
+    assert tf.get_csv_header() == g["header"]
+    assert tf.get_csv_data(data) == g["line"]
+    assert tf.get_csv_footer(data) == g["footer"]
+    path = tmp_path / "SUMMARY.txt"
+    tf.touch_textfile(path)
+    tf.write_textfile(path, data)
+    tf.add_footer_textfile(path, data)
+    assert path.read_text() == g["header"] + g["line"] + "\n" + g["footer"] + "\n"
+
+
+def test_sweep_experiment_list():
+    """main.sweep_experiments mirrors main.py:130-153: 5 x 2 x (2 x 10 + 2 x 10) experiments."""
+    from pnp_pds_b200.main import sweep_experiments
+    ex = sweep_experiments()
+    assert len(ex) == 5 * 2 * 40
+    assert ex[0]["method"] == {"method": "A-Proposed", "max_iter": 1200, "gamma1": 0.99, "gamma2": 0.99, "alpha_n": 0.8 + 0.02}
+    tv = [e for e in ex if e["method"]["method"] == "A-PDS-TV"][0]
+    assert tv["method"]["gamma1"] == 0.125
+    lams = [e["method"]["myLambda"] for e in ex if e["method"]["method"] == "A-RED-DnCNN"][:10]
+    assert lams[-1] == 1.99 and abs(lams[0] - 0.2) < 1e-12
+    assert [e["method"]["max_iter"] for e in ex if e["settings"]["deg_op"] == "random_sampling"][0] == 3000
