@@ -390,10 +390,8 @@ def main():
             mid_kernel = "conv_mid_simt_kernel"
         elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0) > 0:
             mid_kernel = "roll::conv_roll_kernel (row-streaming cta_group::2 body layer, %d-row bands)" % eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0)
-        elif chunk * ((H + 15) // 16) * ((W + 7) // 8) >= 4096:
-            mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
         else:
-            mid_kernel = "conv_tc_kernel<64> (1-CTA tile kernel)"
+            mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
         total_flop = DNCNN_FLOP_PER_PX_MID_LAYER * float(B * H * W) * n_mid_layers * a.steps
         achieved = total_flop / (mid_ms * 1e-3) / 1e12 if mid_n else None
         # DRAM traffic of the body-layer kernel per launch, from the committed ncu --set full capture (bytes per pixel x

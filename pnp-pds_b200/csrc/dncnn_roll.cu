@@ -251,7 +251,8 @@ int roll_setup() {
 
 // Rows per band, or 0 when the tile kernels are the better choice for this launch.  Cost model in units of "one 128-pixel row
 // step of a CTA pair": a band of rb rows costs rb + 2 steps (two halo rows), the launch costs ceil(units / pairs) bands per
-// pair; the 2-CTA tile kernel needs ~1.12 steps per tile pair (it re-reads the A operand, ncu: 3246 vs 2912 cycles).
+// pair; the 2-CTA tile kernel needs ~1.2 steps per tile pair (it re-reads the A operand: 3246 vs 2912 cycles per 128
+// pixels in ncu, and it re-fetches halos; calibrated on single 512x512 and 1024x1024 images).
 // `force`: ignore the comparison with the tile kernels (tests).
 int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
   if (W % roll::kStripW != 0 || H < 8 || nimg < 1) return 0;
@@ -269,7 +270,7 @@ int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
   }
   if (force) return best_rb;
   const long long tile_pairs = ((long long)nimg * ((H + kTileRows - 1) / kTileRows) * ((W + kTileCols - 1) / kTileCols) + 1) / 2;
-  const double tile_cost = 1.12 * (double)((tile_pairs + pairs - 1) / pairs);
+  const double tile_cost = 1.2 * (double)((tile_pairs + pairs - 1) / pairs);
   return (double)best_cost < tile_cost ? best_rb : 0;
 }
 

@@ -213,13 +213,13 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     }
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
-      // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and the launch
-      // has enough row bands for every CTA pair; else the 2-CTA tile kernel for large launches and the 1-CTA tile kernel
-      // for single small images.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width allows,
-      // bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel.
-      const long long ntiles = (long long)nimg * ((d.H + 15) / 16) * ((d.W + 7) / 8);
+      // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and its cost model
+      // (roll_band_rows) beats the tiles; else the 2-CTA tile kernel (measured faster than the 1-CTA one at every size: half
+      // the weight prologue per SM, fewer operand bytes; cfg1 264 vs 285 us per iteration, cfg2 694 vs 792).  The 1-CTA tile
+      // kernel stays as a cross-check.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width
+      // allows, bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel.
       const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
-      const bool two_cta = (h->tc_variant & 32) || (!(h->tc_variant & 16) && ntiles >= 4096);
+      const bool two_cta = !(h->tc_variant & 16);
       if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && band > 0) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {

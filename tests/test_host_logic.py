@@ -217,7 +217,8 @@ def test_row_streaming_band_selection_cost_model():
     f = lib.pds_debug_roll_band_rows
     assert f(8, 1024, 1024, 0) == 64                      # cfg4: 8 images per denoiser pass
     assert 8 <= f(1, 1024, 1024, 0) <= 64                 # one 3x1024x1024 image still fills the CTA pairs
-    assert f(1, 256, 256, 0) == 0 and f(1, 512, 512, 0) == 0     # single small images: too few bands, tiles win
+    assert f(1, 256, 256, 0) == 0                         # a single small image: too few bands, tiles win
+    assert f(1, 512, 512, 0) == 14                        # 37 bands x 2 strip pairs = one band per CTA pair
     assert f(1, 100, 100, 0) == 0 and f(1, 100, 100, 1) == 0      # width not a multiple of 128: never
     assert f(1, 256, 256, 1) >= 8                         # forced (tests)
 
