@@ -52,7 +52,7 @@ enum {
 
 /* engine used for the 64->64 channel layers of the denoiser */
 enum {
-  PDS_CONV_TCGEN05 = 0, /* TMA-fed tcgen05 implicit GEMM, fp16 hi/lo split operands, fp32 TMEM accumulators */
+  PDS_CONV_TCGEN05 = 0, /* TMA-fed tcgen05 implicit GEMM: fp16 product + e4m3 operand corrections, fp32 TMEM accumulators */
   PDS_CONV_SIMT = 1     /* fp32 CUDA-core direct convolution (cross-check engine) */
 };
 

@@ -14,7 +14,7 @@
 //     72 tcgen05.mma per tile (was 108 with three fp16 products) at ~2^-16 relative operand precision;
 //     needed for the 1e-4 iterate gate (single-pass fp16 misses it; tools/emulate_split.py
 //     measures 3e-6 for this scheme against 6e-5 for one fp16 pass on the same loop).
-//   * the activation halo tile (18 rows x 10 pixels x 64 ch, one per hi/lo plane) is fetched by
+//   * the activation halo tile (18 rows x 10 pixels x 128 B, one per plane) is fetched by
 //     ONE 4-D TMA box each with SWIZZLE_128B; out-of-image pixels are zero-filled by TMA, which is
 //     exactly the convolution's zero padding.  All 9 taps read that single tile: the A descriptor
 //     of tap (dy,dx) starts at pixel-row offset (dy*10+dx)*128 B with SBO = one tile row (1280 B).
@@ -211,11 +211,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 // ---------------------------------------------------------------------------------------------
 // First layer (Cin = 1|3 -> 64) on the tensor pipe.  K = 9*Cin <= 27 is padded to 32 (two k-steps); the
-// A operand is an explicit im2col tile that four producer warps build in shared memory: thread m owns
-// pixel m of the 16x8 tile, reads its 3x3xCin window (zero padding, input clamp of denoiser.py:40), splits
-// to fp16 hi/lo and writes the 64 meaningful bytes of its 128-byte row in SWIZZLE_128B order.  MMAs and the
-// epilogue are those of the body layers (N=128 [w_hi;w_lo] for the hi plane, N=64 for the lo plane), so the
-// kernel is bound by writing the 256 B/pixel of activations, not by CUDA-core FMAs.
+// A operand is an explicit im2col tile that two groups of four producer warps build in shared memory: thread m
+// owns pixel m of the 16x8 tile, reads its 3x3xCin window (zero padding, input clamp of denoiser.py:40), splits
+// to fp16 hi/lo and writes the 64 meaningful bytes of its 128-byte row in SWIZZLE_128B order.  With only two
+// k-steps the tensor work is negligible, so this layer keeps three exact fp16 products (N=128 [w_hi;w_lo] against
+// the hi tile, N=64 against the lo tile); the epilogue is the body layers' (fp16 plane + e4m3 plane), on two groups
+// of four warps.  The kernel is bound by issue slots and by writing the 256 B/pixel of activations.
 // ---------------------------------------------------------------------------------------------
 namespace first {
 constexpr int kStages = 4, kThreadsF = 544;                 // 2 x 4 producer warps, 1 MMA warp, 2 x 4 epilogue warps
