@@ -19,6 +19,22 @@ def q16(t): return t.to(torch.float16).to(torch.float64)
 def q8(t): return t.to(torch.float32).to(torch.float8_e4m3fn).to(torch.float64)
 def qbf(t): return t.to(torch.bfloat16).to(torch.float64)
 
+_E2M1 = torch.tensor([0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0], dtype=torch.float64)
+
+
+def q4_block(t, dim):
+    """e2m1 with one power-of-two scale per block of 32 elements along `dim` (mxfp4-style, ue8m0 scales)."""
+    t = t.movedim(dim, -1)
+    shp = t.shape
+    b = t.reshape(*shp[:-1], shp[-1] // 32, 32)
+    amax = b.abs().amax(-1, keepdim=True).clamp_min(1e-300)
+    scale = torch.exp2(torch.ceil(torch.log2(amax / 6.0)))
+    x = (b / scale).abs().clamp(max=6.0)
+    idx = (x.unsqueeze(-1) - _E2M1).abs().argmin(-1)
+    q = _E2M1[idx] * torch.sign(b) * scale
+    return q.reshape(shp).movedim(-1, dim)
+
+
 def make_denoise(layers, scheme, slope=0.01, sign=1.0, clamp=True):
     L = [(torch.from_numpy(w).double(), torch.from_numpy(b).double()) for w, b in layers]
     def conv(a, w): return F.conv2d(a, w, None, padding=1)
@@ -39,6 +55,9 @@ def make_denoise(layers, scheme, slope=0.01, sign=1.0, clamp=True):
             S = 18 - e
             t = conv(q8(a), q8(w_lo * 2.0**S)) + conv(q8(a_lo * 2.0**10), q8(w_hi * 2.0**(S - 10)))
             return conv(a_hi, w_hi) + (t * 2.0**-S).float().double()
+        if scheme == "fp4lo":      # what a block-scaled fp4 correction operand would give (1.5 MMA times per layer)
+            t = conv(q4_block(a, 1), q4_block(w_lo, 1)) + conv(q4_block(a_lo, 1), q4_block(w_hi, 1))
+            return conv(a_hi, w_hi) + t.float().double()
         raise ValueError(scheme)
     def denoise(x):
         squeeze = x.ndim == 2
@@ -89,7 +108,7 @@ def main():
     phi, adj = po.make_operators("blur", h, 1.0)
     x0, obs = po.synthesize_observation(img, "blur", h, 1.0, 0.01, 0.0, False, 100)
     res = {}
-    for scheme in sys.argv[3:] or ["fp32", "fp16x1", "fp16x3", "fp8lo", "fp16x2w"]:
+    for scheme in sys.argv[3:] or ["fp32", "fp16x1", "fp16x3", "fp8lo", "fp16x2w", "fp4lo"]:
         den = make_denoise(layers, scheme)
         x, s, c, psnr, _ = po.pds_iterations(x0, obs, img, phi, adj, den, 0.99, 0.99, 0.9, 0.95, 1.0, 0.01, 0.0, 100, its, "A-Proposed")
         res[scheme] = (x, psnr[-1])
