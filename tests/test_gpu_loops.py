@@ -208,3 +208,33 @@ def test_tv_needs_colour(assets):
     x = np.full((1, 8, 8), 0.5, dtype=np.float32)
     with pytest.raises(ValueError):
         iteration.run_batch(x, x, x, phi, adj, dict(gamma1=0.1, gamma2=0.99), None, 1, "A-PDS-TV", 1)
+
+
+def test_batched_full_loop_tensor_engine_tracks_fp32_engine(assets):
+    """ours-A, blur, 12 gray 256x256 images, 300 iterations: the tcgen05 engine (row-streaming body kernel at this launch
+    size, e4m3 operand corrections) against the fp32 CUDA-core engine on the same inputs — the north-star gates between the
+    two engines at a batched, full-width shape the CPU oracle could not finish in test time."""
+    from pnp_pds_b200 import _lib, iteration, operators
+    from pnp_pds_b200.models.weights import load_weights
+    B, H, W, n_iter = 12, 256, 256, 300
+    assert _lib.load().pds_debug_roll_band_rows(B, H, W, 0) > 0
+    w = load_weights(weights_path("DnCNN_nobn_nch_1_nlev_0.01"))
+    phi, adj = operators.get_observation_operators("blur", assets["blur_1"], 1.0)
+    imgs, x0s, obss = [], [], []
+    for b in range(B):
+        img = O.synthetic_image(40 + b, 1, H, W)
+        x0, obs = O.synthesize_observation(img, "blur", assets["blur_1"], 1.0, 0.01, 0.0, False, 300)
+        imgs.append(img); x0s.append(x0); obss.append(obs)
+    prm = dict(gamma1=0.99, gamma2=0.99, alpha_s=0.95, alpha_n=0.95, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.0, poisson_alpha=300, r=1.0)
+    out = {}
+    for engine in ("tcgen05", "simt"):
+        out[engine] = iteration.run_batch(np.stack(x0s), np.stack(obss), np.stack(imgs), phi, adj, prm, w, n_iter, "ours-A", 1,
+                                          conv_engine=engine)
+    for b in range(B):
+        e = rel_l2(out["tcgen05"]["x"][b], out["simt"]["x"][b])
+        assert e < REL_L2_GATE, (b, e)
+    dpsnr = np.max(np.abs(out["tcgen05"]["psnr"][-1] - out["simt"]["psnr"][-1]))
+    print(f"tensor vs fp32 engine after {n_iter} iterations: max rel_l2 = "
+          f"{max(rel_l2(out['tcgen05']['x'][b], out['simt']['x'][b]) for b in range(B)):.2e}, max dPSNR = {dpsnr:.2e} dB")
+    assert dpsnr < DPSNR_GATE
+    assert np.all(out["tcgen05"]["c"][-1] < 1e-3)                      # converging
