@@ -207,6 +207,26 @@ TV_CASES = [
 ]
 
 
+def gen_textfile():
+    """SUMMARY text-file strings from the reference's own writer (utils/utils_textfile.py) for a fixed `datas` dict."""
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("ref_textfile", os.path.join(ref_harness.REF_ROOT, "utils", "utils_textfile.py"))
+    tf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tf)
+    data = {"experimental_settings": {"deg_op": "blur", "gaussian_nl": 0.01, "poisson_alpha": 300, "r": 0.8, "sp_nl": 0.0, "poisson_noise": False},
+            "method": {"method": "A-Proposed", "gamma1": 0.99, "gamma2": 0.99, "alpha_n": 0.95, "alpha_s": 0.95, "myLambda": 1, "max_iter": 1200,
+                       "m1": 15, "m2": 15, "architecture": "x", "gammaInADMMStep1": 0.1},
+            "configs": {"ch": 3, "add_timestamp": True, "result_output": False},
+            "summary": {"algorithm": "PnP-PDS", "denoiser": "DnCNN", "Average_PSNR": 31.25, "Average_SSIM": 0.91},
+            "results": {0: {"filename": "a.png", "PSNR": 31.0, "SSIM": 0.9, "PSNR_observation": 24.1, "SSIM_observation": 0.6},
+                        1: {"filename": "b.png", "PSNR": 31.5, "SSIM": 0.92, "PSNR_observation": 23.9, "SSIM_observation": 0.58}}}
+    out = {"data": {k: (v if k != "results" else {str(i): r for i, r in v.items()}) for k, v in data.items()},
+           "header": tf.get_csv_header(), "line": tf.get_csv_data(data), "footer": tf.get_csv_footer(data)}
+    json.dump(out, open(os.path.join(HERE, "textfile.json"), "w"), indent=1)
+    print("wrote textfile.json")
+
+
 def run_case(ref, case, snapshots):
     """Mirrors main.test_all_images main.py:41-69 (observation synthesis, call into test_iter)."""
     op, un = ref.operators, ref.utils_noise
@@ -265,7 +285,7 @@ def main():
     ref = ref_harness.load()
     import torch
     torch.set_num_threads(os.cpu_count())
-    todo = a.only.split(",") if a.only else ["assets", "ops", "noise", "denoiser", "loops", "tv"]
+    todo = a.only.split(",") if a.only else ["assets", "ops", "noise", "denoiser", "loops", "tv", "textfile"]
     if "assets" in todo:
         gen_assets(ref)
     if "ops" in todo:
@@ -276,6 +296,8 @@ def main():
         gen_denoiser(ref)
     if "loops" in todo:
         gen_loops(ref, LOOP_CASES, "loops.npz", snapshots=(1, 2, 10))
+    if "textfile" in todo:
+        gen_textfile()
     if "tv" in todo:
         gen_loops(ref, TV_CASES, "tv.npz", snapshots=(1, 2, 10))
     if a.long or "long" in todo:
