@@ -36,7 +36,9 @@ constexpr uint32_t kIdescN64 = (1u << 4) | ((256u >> 4) << 24) | ((64u >> 3) << 
 struct RollArgs {
   const __half* w_img;
   const float* bias;
+  const __half* in;       // input activations (conv_roll_d_kernel reads the a_lo half of plane 1 with plain loads)
   __half* out;
+  int write_a8;           // see store_half_row (tc_common.cuh)
   float slope, lo_scale;
   int H, W, nimg;
   int band_rows, nbands, npairs_x, nunits;
@@ -222,9 +224,284 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           const size_t pix = (size_t)(yb + jr) * a.W + x;
           __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
           uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
-          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
-          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
+          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale, a.write_a8);
+          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale, a.write_a8);
         }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  two::cluster_sync_all();                  // the peer may still be reading TMEM / signalling our barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Same layer, with the e4m3(a) operand rebuilt on chip ("derive" form, the default).
+// Plane 1 of the activations is [e4m3(fp16(v)) x 64 | e4m3((v - fp16(v)) 2^10) x 64]: its first half is a function of plane 0,
+// so storing and re-loading it costs 128 of the layer's 512 HBM bytes per pixel for nothing.  Here
+//   * the TMA producer of each CTA lands only the fp16 row (plane 0) in the "F" slot of a ring stage (local full barrier);
+//   * four converter warps per CTA build the "E" slot of the stage — the K = 128 e4m3 operand row in the SWIZZLE_128B layout the
+//     MMA descriptors expect: bytes 0..63 = cvt.rn.satfinite.e4m3x2.f16x2 of the F row (read back from shared memory), bytes
+//     64..127 = the a_lo half of plane 1, fetched with plain 16-byte loads (ld.global.L2::64B, so that DRAM does not deliver
+//     the unused half of the 128-byte line) one row ahead, zero outside the image like TMA; then fence.proxy.async (every
+//     writing lane) + one relaxed cluster-scope arrive per warp on the stage's "ready" barrier in CTA 0.  Relaxed on
+//     purpose, as for the TMEM-drained signal: a release at cluster scope compiles to MEMBAR.ALL.GPU per warp and row, and
+//     the writes it would order are already performed (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC of the proxy fence);
+//   * two converter warps, not four: with 8 warps per CTA every scheduler holds two and the register cap stays at 255; with
+//     10 warps it drops to 168, ptxas spills in the MMA-issue loop and the tensor pipe starves (measured: 1.43 vs 1.12 ms);
+//   * the F ring (5 slots) is one deeper than the E ring (4), so the row loads run ahead of the converters;
+//   * the MMA issuer waits for "ready" only (it implies that both F rows have landed), and frees F and E separately;
+//   * the layers feeding this kernel skip the e4m3(a) store (write_a8 = 0): 384 instead of 512 HBM bytes per pixel and layer.
+// MMA order, accumulators and epilogue are those of conv_roll_kernel, and e4m3(fp16(v)) is what every producer stores, so the
+// result is bit-identical to the other body kernels.
+// ---------------------------------------------------------------------------------------------
+constexpr int kConvWarps = 2;                             // 8 warps per CTA = 2 per scheduler: the register cap stays at 255 (10 warps: 168, spills)
+constexpr int kConvThreads = 32 * kConvWarps;
+constexpr int kThreadsD = kThreads + kConvThreads;
+constexpr int kConvTasks = (4 * kRowPix + kConvThreads - 1) / kConvThreads;   // 16-byte e4m3 chunks per thread and row (9)
+constexpr int kFD = 5, kED = 4;                           // F ring (fp16 rows, TMA) one deeper than the E ring (e4m3 rows, converters)
+constexpr uint32_t kOffED = kOffAR + kFD * kRowSlot, kOffBarD = kOffED + kED * kRowSlot;
+constexpr uint32_t kOffBiasD = kOffBarD + 256, kSmemBytesD = kOffBiasD + 256 + 1024;
+static_assert(kSmemBytesD <= 227 * 1024, "shared memory budget");
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.L2::64B.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
+    conv_roll_d_kernel(const __grid_constant__ CUtensorMap tmap, RollArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t sW = base, sF = base + kOffAR, sE = base + kOffED, sBar = base + kOffBarD;
+  // barriers: fullF[5] @0 (local), emptyF[5] @40 (local), emptyE[4] @80 (local), ready[4] @112 (CTA 0), wfull @144,
+  //           tfull[4] @152, tempty[4] @184 (CTA 0), tmem slot @216
+  const uint32_t bFullF = sBar, bEmptyF = sBar + 40, bEmptyE = sBar + 80, bReady = sBar + 112, bW = sBar + 144;
+  const uint32_t bTFull = sBar + 152, bTEmpty = sBar + 184, sTmemSlot = sBar + 216;
+  float* bias_s = reinterpret_cast<float*>(gbase + kOffBiasD);
+  const uint32_t rank = two::cluster_rank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFD; ++i) {
+      mbar_init(bFullF + 8 * i, 1);         // this CTA's producer: arrive.expect_tx for its own row box
+      mbar_init(bEmptyF + 8 * i, 1 + kConvWarps);   // multicast commit of the fp16 MMAs + this CTA's converter warps
+    }
+    for (int i = 0; i < kED; ++i) {
+      mbar_init(bEmptyE + 8 * i, 1);        // multicast commit of the e4m3 MMAs
+      mbar_init(bReady + 8 * i, 2 * kConvWarps);   // converter warps of both CTAs (used in CTA 0)
+    }
+    mbar_init(bW, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 8);        // 4 epilogue warps x 2 CTAs arrive on CTA 0's barrier
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();                          // barriers initialised, TMEM slot written
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(bW, kWHalf);           // this CTA's half of the weight image
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(a.w_img) + (size_t)rank * kWHalf;
+      for (int i = 0; i < 9; ++i) bulk_load(sW + i * 8192u, src + (size_t)i * 8192u, 8192u, bW);
+    }
+    __syncwarp();
+    mbar_wait(bW, 0);
+  }
+  __syncthreads();
+  two::cluster_sync_all();                  // both halves of the weights landed; all barriers of both CTAs are initialised
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarD + 216);
+  pdl_launch_dependents();
+
+  const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: this CTA's fp16 rows
+    pdl_wait_prior_grid();
+    uint32_t j = 0;
+    for (int unit = cid; unit < a.nunits; unit += nclusters) {
+      const int px = unit % a.npairs_x, t = unit / a.npairs_x;
+      const int band = t % a.nbands, img = t / a.nbands;
+      const int yb = band * a.band_rows;
+      const int rb = min(a.band_rows, a.H - yb);
+      const int x0 = (px * 2 + (int)rank) * kStripW;
+      for (int s = 0; s < rb + 2; ++s, ++j) {
+        const uint32_t fs = j % kFD, fuse = j / kFD;
+        mbar_wait(bEmptyF + 8 * fs, (fuse & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(bFullF + 8 * fs, kRowBytes);
+          tma_load_4d(sF + fs * kRowSlot, &tmap, bFullF + 8 * fs, 0, x0 - 1, yb - 1 + s, img * 2);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (CTA 0 only)
+    if (rank == 0) {
+      const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
+      uint32_t j = 0;
+      uint32_t n0 = 0;                      // output rows started so far by this cluster: row n lives in TMEM block n & 3
+      for (int unit = cid; unit < a.nunits; unit += nclusters) {
+        const int band = (unit / a.npairs_x) % a.nbands;
+        const int rb = min(a.band_rows, a.H - band * a.band_rows);
+        for (int s = 0; s < rb + 2; ++s, ++j) {
+          // input row yb-1+s feeds output rows s-2 (dy=2), s-1 (dy=1), s (dy=0) of the band
+          const int mask = (s >= 2 ? 4 : 0) | ((s >= 1 && s <= rb) ? 2 : 0) | (s < rb ? 1 : 0);
+          const uint32_t nn = n0 + (uint32_t)s;
+          if (mask & 1) mbar_wait(bTEmpty + 8 * (nn & 3), ((nn >> 2) & 1) ^ 1);      // block of the row started here is drained
+          const uint32_t d0 = tmem_base + (nn & 3) * 128u, d1 = tmem_base + ((nn - 1) & 3) * 128u, d2 = tmem_base + ((nn - 2) & 3) * 128u;
+          const uint32_t fs = j % kFD, es = j % kED, euse = j / kED;
+          mbar_wait(bReady + 8 * es, euse & 1);                           // E rows of both CTAs written (=> both F rows landed)
+          tc_fence_after();
+          const uint32_t f_lo = (((sF + fs * kRowSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t e_lo = (((sE + es * kRowSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (elect_one()) {
+            issue_row_masked<true>(mask, d2, d1, d0, f_lo, w_lo);
+            two::umma_commit_2sm(bEmptyF + 8 * fs);
+            issue_row_masked<false>(mask, d2, d1, d0, e_lo, w_lo);
+            two::umma_commit_2sm(bEmptyE + 8 * es);
+            if (mask & 4) two::umma_commit_2sm(bTFull + 8 * ((nn - 2) & 3));        // output row s-2 is complete
+          }
+          __syncwarp();
+        }
+        n0 += (uint32_t)rb;
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------ epilogue (each CTA drains its own 128 TMEM lanes = pixels)
+    const int q = warp & 3;
+    const int t = q * 32 + lane;
+    const size_t hw = (size_t)a.H * a.W;
+    const uint32_t tempty0 = two::map_to_cta(bTEmpty, 0);
+    uint32_t n = 0;
+    for (int unit = cid; unit < a.nunits; unit += nclusters) {
+      const int px = unit % a.npairs_x, tt = unit / a.npairs_x;
+      const int band = tt % a.nbands, img = tt / a.nbands;
+      const int yb = band * a.band_rows;
+      const int rb = min(a.band_rows, a.H - yb);
+      const int x = (px * 2 + (int)rank) * kStripW + t;
+      for (int jr = 0; jr < rb; ++jr, ++n) {
+        const uint32_t blk = n & 3;
+        mbar_wait(bTFull + 8 * blk, (n >> 2) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 128u;
+        uint32_t r0[32], r1[32], r2[32], r3[32];
+        tmem_ld32(taddr + 0, r0);
+        tmem_ld32(taddr + 64, r2);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld32(taddr + 96, r3);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) two::mbar_arrive_cluster(tempty0 + 8 * blk);      // block released before any arithmetic or store
+        if (x < a.W) {
+          const size_t pix = (size_t)(yb + jr) * a.W + x;
+          __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+          uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale, a.write_a8);
+          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale, a.write_a8);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ converters: build the e4m3 operand row of every stage
+    const int tc = (int)threadIdx.x - kThreads;                          // 0..kConvThreads-1
+    const size_t hw = (size_t)a.H * a.W;
+    const uint32_t ready0 = two::map_to_cta(bReady, 0);
+    // Task k < 8 of this thread: pixel group g = kConvWarps k + (warp - 6) (8 consecutive pixels of the row box), 16-channel
+    // quarter lane & 3; a quarter-warp (one 128-byte shared-memory transaction of the 16-byte accesses) covers the two pixels
+    // {i, i ^ 5} of the group: their swizzle phases differ in bit 0 (the two fp16 reads land in disjoint 16-byte columns) and in
+    // bit 2 (so do the two e4m3 writes) — no bank conflicts.  Task 8 (threads 0..7): the two halo pixels 128, 129.
+    constexpr int kFull = kConvTasks - 1;                                // tasks that every thread has
+    const int tail = tc < 4 * kRowPix - kFull * kConvThreads;            // this thread has the last task too
+    const int pig = ((lane >> 2) & 1) ? ((lane >> 3) ^ 5) : (lane >> 3);
+    const uint32_t qd = (uint32_t)lane & 3u;
+    auto task_px = [&](int k) { return k < kFull ? (kConvWarps * k + (warp - 6)) * 8 + pig : 128 + (tc >> 2); };
+    pdl_wait_prior_grid();                                               // plain loads of the previous layer's output below
+    uint32_t j = 0;
+    for (int unit = cid; unit < a.nunits; unit += nclusters) {
+      const int px = unit % a.npairs_x, tt = unit / a.npairs_x;
+      const int band = tt % a.nbands, img = tt / a.nbands;
+      const int yb = band * a.band_rows;
+      const int rb = min(a.band_rows, a.H - yb);
+      const int x0 = (px * 2 + (int)rank) * kStripW - 1;                 // image x of box pixel 0
+      const uint8_t* p1 = reinterpret_cast<const uint8_t*>(a.in) + ((size_t)img * 2 + 1) * hw * 128 + 64 + qd * 16;
+      uint4 lo[kConvTasks];
+      auto fetch = [&](int s) {                                          // a_lo chunks of input row yb-1+s (zero outside the image)
+        const int y = yb - 1 + s;
+        const bool yok = y >= 0 && y < a.H;
+#pragma unroll
+        for (int k = 0; k < kConvTasks; ++k) {
+          const int x = x0 + task_px(k);
+          const bool ok = yok && (k < kFull || tail) && x >= 0 && x < a.W;
+          lo[k] = ok ? ldg128(p1 + ((size_t)y * a.W + x) * 128) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      fetch(0);
+      for (int s = 0; s < rb + 2; ++s, ++j) {
+        const uint32_t fs = j % kFD, fuse = j / kFD, es = j % kED, euse = j / kED;
+        const uint32_t F = sF + fs * kRowSlot, E = sE + es * kRowSlot;
+        mbar_wait(bFullF + 8 * fs, fuse & 1);                            // fp16 row landed
+        mbar_wait(bEmptyE + 8 * es, (euse & 1) ^ 1);                     // e4m3 MMAs of the previous use are done
+#pragma unroll
+        for (int k0 = 0; k0 < kConvTasks; k0 += 4) {                     // batches of 4 tasks: 8 shared-memory reads in flight
+          uint4 h0[4], h1[4];
+#pragma unroll
+          for (int k = k0; k < k0 + 4 && k < kConvTasks; ++k) {
+            if (k < kFull || tail) {
+              const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
+              h0[k - k0] = lds128(F + p * 128u + (((2u * qd) ^ sw) << 4));
+              h1[k - k0] = lds128(F + p * 128u + (((2u * qd + 1u) ^ sw) << 4));
+            }
+          }
+#pragma unroll
+          for (int k = k0; k < k0 + 4 && k < kConvTasks; ++k) {
+            if (k < kFull || tail) {
+              const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
+              uint4 a8;
+              a8.x = e4m3x2_from_f16x2(h0[k - k0].x) | (e4m3x2_from_f16x2(h0[k - k0].y) << 16);
+              a8.y = e4m3x2_from_f16x2(h0[k - k0].z) | (e4m3x2_from_f16x2(h0[k - k0].w) << 16);
+              a8.z = e4m3x2_from_f16x2(h1[k - k0].x) | (e4m3x2_from_f16x2(h1[k - k0].y) << 16);
+              a8.w = e4m3x2_from_f16x2(h1[k - k0].z) | (e4m3x2_from_f16x2(h1[k - k0].w) << 16);
+              sts128(E + p * 128u + ((qd ^ sw) << 4), a8);
+            }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kConvTasks; ++k) {
+          if (k < kFull || tail) {
+            const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
+            sts128(E + p * 128u + (((4u + qd) ^ sw) << 4), lo[k]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bEmptyF + 8 * fs);                                 // this warp no longer reads F
+          two::mbar_arrive_cluster(ready0 + 8 * es);
+        }
+        if (s + 1 < rb + 2) fetch(s + 1);                                // next row's a_lo: in flight while the barriers are awaited
       }
     }
   }
@@ -242,6 +519,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 
 int roll_setup() {
   cudaError_t e = cudaFuncSetAttribute(roll::conv_roll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roll::kSmemBytesR);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(roll::conv_roll_d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)roll::kSmemBytesD);
   if (e != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(conv_roll_kernel): ") + cudaGetErrorString(e));
     return 1;
@@ -274,11 +553,14 @@ int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
   return (double)best_cost < tile_cost ? best_rb : 0;
 }
 
-cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, cudaStream_t st) {
+cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, int derive,
+                                 int write_a8, cudaStream_t st) {
   roll::RollArgs a{};
   a.w_img = L.w_mid_tc2;
   a.bias = L.bias;
+  a.in = plan->act[in_buf];
   a.out = plan->act[in_buf ^ 1];
+  a.write_a8 = write_a8;
   a.slope = slope;
   a.lo_scale = L.lo_scale;
   a.H = plan->H;
@@ -289,6 +571,7 @@ cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_ro
   a.npairs_x = (plan->W + 2 * roll::kStripW - 1) / (2 * roll::kStripW);
   a.nunits = nimg * a.nbands * a.npairs_x;
   const int nclusters = a.nunits < plan->num_sms / 2 ? a.nunits : plan->num_sms / 2;
+  if (derive) return launch_pdl(roll::conv_roll_d_kernel, 2 * nclusters, roll::kThreadsD, roll::kSmemBytesD, st, plan->map_row[in_buf], a);
   return launch_pdl(roll::conv_roll_kernel, 2 * nclusters, kThreads, roll::kSmemBytesR, st, plan->map_row[in_buf], a);
 }
 

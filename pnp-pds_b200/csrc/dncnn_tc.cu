@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const size_t pix = (size_t)y * a.W + x;
         __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
         uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
-        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
-        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
+        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale, a.write_a8);
+        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale, a.write_a8);
       }
     }
   }
@@ -235,6 +235,7 @@ struct FirstArgs {
   __half* out;
   float slope;
   int clamp_in;
+  int write_a8;           // see store_half_row (tc_common.cuh)
   int H, W, nimg, tiles_x, tiles_y, ntiles;
 };
 
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
         tmem_ld32(taddr, r0);
         tmem_ld32(taddr + 64, r2);
         tmem_ld_wait();
-        if (st) store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, 1.f);      // columns [64,128) hold a_hi*w_lo at scale 1
+        if (st) store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, 1.f, a.write_a8);      // columns [64,128) hold a_hi*w_lo at scale 1
       }
       {
         uint32_t r1[32], r3[32];
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
-        if (st) store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, 1.f);
+        if (st) store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, 1.f, a.write_a8);
       }
     }
   }
@@ -792,8 +793,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);      // stage released before any arithmetic or store
       if (st) {
-        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale);
-        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale);
+        store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale, a.write_a8);
+        store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale, a.write_a8);
       }
     }
   }
@@ -989,6 +990,7 @@ cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLa
   a.out = plan->act[in_buf ^ 1];
   a.slope = slope;
   a.lo_scale = L.lo_scale;
+  a.write_a8 = 1;
   a.C = 64;
   fill_common(a, plan, nimg);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
@@ -1002,6 +1004,7 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
   a.out = plan->act[in_buf ^ 1];
   a.slope = slope;
   a.lo_scale = L.lo_scale;
+  a.write_a8 = 1;
   a.C = 64;
   fill_common(a, plan, nimg);
   const int npairs = (a.ntiles + 1) / 2;
@@ -1010,7 +1013,7 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
 }
 
 cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
-                                 cudaStream_t st) {
+                                 int write_a8, cudaStream_t st) {
   first::FirstArgs a{};
   a.in = in;
   a.w_img = L.w_first_tc;
@@ -1018,6 +1021,7 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
   a.out = plan->act[0];
   a.slope = slope;
   a.clamp_in = clamp_in;
+  a.write_a8 = write_a8;
   a.H = plan->H;
   a.W = plan->W;
   a.nimg = nimg;

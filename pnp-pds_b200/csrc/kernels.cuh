@@ -116,8 +116,9 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
 void tc_plan_destroy(TcPlan* p);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
+// write_a8: also store the e4m3(fp16(v)) half of plane 1 (0 when the next layer is the row-streaming kernel, which rebuilds it)
 cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
-                                 cudaStream_t st);
+                                 int write_a8, cudaStream_t st);
 cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
                                 float residual_sign, int clamp, float* out, cudaStream_t st);
@@ -125,6 +126,8 @@ int tc_num_sms();
 // row-streaming body layer (dncnn_roll.cu): band height for a launch of nimg images (0 = not applicable, use the tile kernels)
 int roll_setup();
 int roll_band_rows(int nimg, int H, int W, int num_sms, bool force);
-cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, cudaStream_t st);
+// derive: 1 = rebuild e4m3(fp16(v)) from plane 0 on chip (input layers may skip that store), 0 = read it from plane 1
+cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, int derive,
+                                 int write_a8, cudaStream_t st);
 
 }  // namespace pds

@@ -206,22 +206,26 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const int nimg = (d.B - b0 < h->chunk) ? d.B - b0 : h->chunk;
     const float* cin = in + (size_t)b0 * d.n;
     float* cout = out + (size_t)b0 * d.n;
+    // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and its cost model
+    // (roll_band_rows) beats the tiles; else the 2-CTA tile kernel (measured faster than the 1-CTA one at every size: half
+    // the weight prologue per SM, fewer operand bytes; cfg1 264 vs 285 us per iteration, cfg2 694 vs 792).  The 1-CTA tile
+    // kernel stays as a cross-check.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width
+    // allows, bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel, bit 8 makes the row-streaming kernel read e4m3(a) from
+    // HBM instead of rebuilding it on chip (then every layer stores it).
+    const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
+    const bool two_cta = !(h->tc_variant & 16);
+    const bool derive = band > 0 && !(h->tc_variant & 256);
     if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
-      PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, st));
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, derive ? 0 : 1, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     }
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
-      // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and its cost model
-      // (roll_band_rows) beats the tiles; else the 2-CTA tile kernel (measured faster than the 1-CTA one at every size: half
-      // the weight prologue per SM, fewer operand bytes; cfg1 264 vs 285 us per iteration, cfg2 694 vs 792).  The 1-CTA tile
-      // kernel stays as a cross-check.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width
-      // allows, bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel.
-      const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
-      const bool two_cta = !(h->tc_variant & 16);
       if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && band > 0) {
-        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, st));
+        // the last layer reads the full plane 1 through TMA, so the body layer feeding it stores e4m3(a)
+        const int write_a8 = (!derive || l == h->depth - 2) ? 1 : 0;
+        PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, derive ? 1 : 0, write_a8, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
       } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {

@@ -35,6 +35,7 @@ struct TcArgs {
   float lo_scale;         // 2^-S of this layer's e4m3 correction accumulator
   int H, W, nimg, tiles_x, tiles_y, ntiles;
   // last layer only
+  int write_a8;           // body / first layer: also store e4m3(fp16(v)) (0 when the consumer rebuilds it: row-streaming kernel)
   const float* net_in;    // (nimg, C, H, W) network input (residual)
   float* out_f32;         // (nimg, C, H, W)
   int C;
@@ -137,17 +138,25 @@ __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float
   const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
   return lo | (hi << 16);
 }
+// two fp16 values -> two e4m3 bytes (low half -> low byte), round to nearest even, saturating
+__device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+  return r;
+}
 
 // 32 channels [c0, c0+32) of one pixel: v = d0 + lo_scale*d1 + bias -> LeakyReLU, written as full 32-byte sectors:
 //   plane 0 (dst_p0, fp16 x 64):  fp16(v) at channels c0..c0+31                         (two 256-bit stores)
-//   plane 1 (dst_p1, 128 bytes):  e4m3(v) at byte c0.., e4m3((v - fp16(v)) * 2^10) at byte 64+c0..   (one 256-bit store each)
+//   plane 1 (dst_p1, 128 bytes):  e4m3(fp16(v)) at byte c0.. (only if write_a8), e4m3((v - fp16(v)) * 2^10) at byte 64+c0..
+// The first half of plane 1 is a function of plane 0 alone, so a consumer can rebuild it on chip: the row-streaming body
+// kernel does (dncnn_roll.cu), and the layers feeding it skip the store (write_a8 = 0: 192 instead of 256 bytes per pixel).
 __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
-                                               const float* bias_s, int c0, float slope, float lo_scale) {
+                                               const float* bias_s, int c0, float slope, float lo_scale, int write_a8) {
   uint32_t a8[8], l8[8];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint32_t hi[8];
-    float v[16], l[16];
+    float l[16];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = q * 16 + 2 * k;
@@ -159,19 +168,17 @@ __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, 
       const __half2 hh = __floats2half2_rn(v0, v1);
       const float2 hf = __half22float2(hh);
       hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      v[2 * k] = v0;
-      v[2 * k + 1] = v1;
       l[2 * k] = (v0 - hf.x) * kActLoScale;
       l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
     }
     st_global_256(dst_p0 + c0 + q * 16, hi);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      a8[q * 4 + k] = pack_e4m3x4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      a8[q * 4 + k] = e4m3x2_from_f16x2(hi[2 * k]) | (e4m3x2_from_f16x2(hi[2 * k + 1]) << 16);
       l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
     }
   }
-  st_global_256(dst_p1 + c0, a8);
+  if (write_a8) st_global_256(dst_p1 + c0, a8);
   st_global_256(dst_p1 + 64 + c0, l8);
 }
 

@@ -118,11 +118,14 @@ def test_row_streaming_body_kernel_matches_tile_kernels(shape):
     w = load_weights(weights_path(SIMPLE[1] if C == 3 else SIMPLE[0]))
     x = np.random.default_rng(11).random(shape).astype(np.float32)
     outs = {}
-    for name, variant in (("roll", 64), ("tile", 128)):      # force / forbid row streaming (the cost model may pick either)
+    # force / forbid row streaming (the cost model may pick either); bit 8: the row-streaming kernel reads e4m3(a) from HBM
+    # instead of rebuilding it from the fp16 plane in shared memory (then every layer stores it)
+    for name, variant in (("roll", 64), ("roll_hbm", 64 | 256), ("tile", 128)):
         with Engine(B, C, H, W, conv_engine="tcgen05") as e:
             e.load_dncnn(w)
             e.set_tc_variant(variant)
             outs[name] = e.dncnn_forward(e.to_device(x)).cpu().numpy()
+    assert np.array_equal(outs["roll"], outs["roll_hbm"])      # same operands bit for bit, same MMA order
     err = float(np.max(np.abs(outs["roll"] - outs["tile"])))
     print(shape, "roll vs tile", err)
     assert err < 2e-6                      # fp32 accumulation order only
