@@ -389,7 +389,9 @@ def main():
         if a.engine != "tcgen05":
             mid_kernel = "conv_mid_simt_kernel"
         elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0) > 0:
-            mid_kernel = "roll::conv_roll_kernel (row-streaming cta_group::2 body layer, %d-row bands)" % eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0)
+            hbm = bool(int(os.environ.get("PDS_TC_VARIANT", "0")) & 256)
+            mid_kernel = ("roll::conv_roll_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand read from HBM)" if hbm else
+                          "roll::conv_roll_d_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand rebuilt on chip from the fp16 row)")
         else:
             mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
         total_flop = DNCNN_FLOP_PER_PX_MID_LAYER * float(B * H * W) * n_mid_layers * a.steps

@@ -41,7 +41,28 @@ struct RollArgs {
   int write_a8;           // see store_half_row (tc_common.cuh)
   float slope, lo_scale;
   int H, W, nimg;
-  int band_rows, nbands, npairs_x, nunits;
+  int npairs_x;           // 256-pixel strip pairs per image row
+  int total_rows;         // nimg * npairs_x * H: rows of all strip-pair columns, column after column
+  int rows_per_cluster;   // contiguous share of that sequence owned by one CTA pair
+};
+
+// The work of one CTA pair: rows [cid * rows_per_cluster, ...) of the global row sequence, cut into bands at the column
+// (image / strip pair) boundaries.  Every pair gets the same number of rows (+ two halo rows per band), so there is no wave
+// quantisation: a fixed band height of 64 on 74 pairs costs 462 row steps per pair at the cfg4 shape, this split 447.
+struct BandWalk {
+  int g, end, H, npairs_x;
+  __device__ __forceinline__ BandWalk(const RollArgs& a, int cid)
+      : g(cid * a.rows_per_cluster), end(min(a.total_rows, (cid + 1) * a.rows_per_cluster)), H(a.H), npairs_x(a.npairs_x) {}
+  __device__ __forceinline__ bool next(int& img, int& px, int& yb, int& rb) {
+    if (g >= end) return false;
+    const int col = g / H;
+    yb = g - col * H;
+    rb = min(H - yb, end - g);
+    img = col / npairs_x;
+    px = col - img * npairs_x;
+    g += rb;
+    return true;
+  }
 };
 
 // All MMAs of one plane of one input row.  MASK bit 2/1/0: the output rows r-1 / r / r+1 (taps dy = 2 / 1 / 0) exist in
@@ -135,17 +156,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarR + 200);
   pdl_launch_dependents();
 
-  const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int cid = blockIdx.x >> 1;
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs; boxes signal CTA 0's full barrier)
     pdl_wait_prior_grid();
     const uint32_t full0 = two::map_to_cta(bFull, 0);
     uint32_t j = 0;
-    for (int unit = cid; unit < a.nunits; unit += nclusters) {
-      const int px = unit % a.npairs_x, t = unit / a.npairs_x;
-      const int band = t % a.nbands, img = t / a.nbands;
-      const int yb = band * a.band_rows;
-      const int rb = min(a.band_rows, a.H - yb);
+    BandWalk walk(a, cid);
+    for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
       const int x0 = (px * 2 + (int)rank) * kStripW;
       for (int s = 0; s < rb + 2; ++s) {
 #pragma unroll
@@ -166,9 +184,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
       uint32_t j = 0;
       uint32_t n0 = 0;                      // output rows started so far by this cluster: row n lives in TMEM block n & 3
-      for (int unit = cid; unit < a.nunits; unit += nclusters) {
-        const int band = (unit / a.npairs_x) % a.nbands;
-        const int rb = min(a.band_rows, a.H - band * a.band_rows);
+      BandWalk walk(a, cid);
+      for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
         for (int s = 0; s < rb + 2; ++s) {
           // input row yb-1+s feeds output rows s-2 (dy=2), s-1 (dy=1), s (dy=0) of the band
           const int mask = (s >= 2 ? 4 : 0) | ((s >= 1 && s <= rb) ? 2 : 0) | (s < rb ? 1 : 0);
@@ -200,11 +217,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     const size_t hw = (size_t)a.H * a.W;
     const uint32_t tempty0 = two::map_to_cta(bTEmpty, 0);
     uint32_t n = 0;
-    for (int unit = cid; unit < a.nunits; unit += nclusters) {
-      const int px = unit % a.npairs_x, tt = unit / a.npairs_x;
-      const int band = tt % a.nbands, img = tt / a.nbands;
-      const int yb = band * a.band_rows;
-      const int rb = min(a.band_rows, a.H - yb);
+    BandWalk walk(a, cid);
+    for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
       const int x = (px * 2 + (int)rank) * kStripW + t;
       for (int jr = 0; jr < rb; ++jr, ++n) {
         const uint32_t blk = n & 3;
@@ -335,16 +349,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarD + 216);
   pdl_launch_dependents();
 
-  const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+  const int cid = blockIdx.x >> 1;
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: this CTA's fp16 rows
     pdl_wait_prior_grid();
     uint32_t j = 0;
-    for (int unit = cid; unit < a.nunits; unit += nclusters) {
-      const int px = unit % a.npairs_x, t = unit / a.npairs_x;
-      const int band = t % a.nbands, img = t / a.nbands;
-      const int yb = band * a.band_rows;
-      const int rb = min(a.band_rows, a.H - yb);
+    BandWalk walk(a, cid);
+    for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
       const int x0 = (px * 2 + (int)rank) * kStripW;
       for (int s = 0; s < rb + 2; ++s, ++j) {
         const uint32_t fs = j % kFD, fuse = j / kFD;
@@ -362,9 +373,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
       const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
       uint32_t j = 0;
       uint32_t n0 = 0;                      // output rows started so far by this cluster: row n lives in TMEM block n & 3
-      for (int unit = cid; unit < a.nunits; unit += nclusters) {
-        const int band = (unit / a.npairs_x) % a.nbands;
-        const int rb = min(a.band_rows, a.H - band * a.band_rows);
+      BandWalk walk(a, cid);
+      for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
         for (int s = 0; s < rb + 2; ++s, ++j) {
           // input row yb-1+s feeds output rows s-2 (dy=2), s-1 (dy=1), s (dy=0) of the band
           const int mask = (s >= 2 ? 4 : 0) | ((s >= 1 && s <= rb) ? 2 : 0) | (s < rb ? 1 : 0);
@@ -395,11 +405,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
     const size_t hw = (size_t)a.H * a.W;
     const uint32_t tempty0 = two::map_to_cta(bTEmpty, 0);
     uint32_t n = 0;
-    for (int unit = cid; unit < a.nunits; unit += nclusters) {
-      const int px = unit % a.npairs_x, tt = unit / a.npairs_x;
-      const int band = tt % a.nbands, img = tt / a.nbands;
-      const int yb = band * a.band_rows;
-      const int rb = min(a.band_rows, a.H - yb);
+    BandWalk walk(a, cid);
+    for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
       const int x = (px * 2 + (int)rank) * kStripW + t;
       for (int jr = 0; jr < rb; ++jr, ++n) {
         const uint32_t blk = n & 3;
@@ -440,11 +447,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
     auto task_px = [&](int k) { return k < kFull ? (kConvWarps * k + (warp - 6)) * 8 + pig : 128 + (tc >> 2); };
     pdl_wait_prior_grid();                                               // plain loads of the previous layer's output below
     uint32_t j = 0;
-    for (int unit = cid; unit < a.nunits; unit += nclusters) {
-      const int px = unit % a.npairs_x, tt = unit / a.npairs_x;
-      const int band = tt % a.nbands, img = tt / a.nbands;
-      const int yb = band * a.band_rows;
-      const int rb = min(a.band_rows, a.H - yb);
+    BandWalk walk(a, cid);
+    for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
       const int x0 = (px * 2 + (int)rank) * kStripW - 1;                 // image x of box pixel 0
       const uint8_t* p1 = reinterpret_cast<const uint8_t*>(a.in) + ((size_t)img * 2 + 1) * hw * 128 + 64 + qd * 16;
       uint4 lo[kConvTasks];
@@ -464,35 +468,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
         const uint32_t F = sF + fs * kRowSlot, E = sE + es * kRowSlot;
         mbar_wait(bFullF + 8 * fs, fuse & 1);                            // fp16 row landed
         mbar_wait(bEmptyE + 8 * es, (euse & 1) ^ 1);                     // e4m3 MMAs of the previous use are done
+        {
+          uint4 h0[kConvTasks], h1[kConvTasks];
 #pragma unroll
-        for (int k0 = 0; k0 < kConvTasks; k0 += 4) {                     // batches of 4 tasks: 8 shared-memory reads in flight
-          uint4 h0[4], h1[4];
-#pragma unroll
-          for (int k = k0; k < k0 + 4 && k < kConvTasks; ++k) {
+          for (int k = 0; k < kConvTasks; ++k) {                         // all shared-memory reads of the row in flight at once
             if (k < kFull || tail) {
               const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
-              h0[k - k0] = lds128(F + p * 128u + (((2u * qd) ^ sw) << 4));
-              h1[k - k0] = lds128(F + p * 128u + (((2u * qd + 1u) ^ sw) << 4));
+              h0[k] = lds128(F + p * 128u + (((2u * qd) ^ sw) << 4));
+              h1[k] = lds128(F + p * 128u + (((2u * qd + 1u) ^ sw) << 4));
             }
           }
 #pragma unroll
-          for (int k = k0; k < k0 + 4 && k < kConvTasks; ++k) {
+          for (int k = 0; k < kConvTasks; ++k) {                         // a_lo half (loaded a row ago) while they return
+            if (k < kFull || tail) {
+              const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
+              sts128(E + p * 128u + (((4u + qd) ^ sw) << 4), lo[k]);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < kConvTasks; ++k) {
             if (k < kFull || tail) {
               const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
               uint4 a8;
-              a8.x = e4m3x2_from_f16x2(h0[k - k0].x) | (e4m3x2_from_f16x2(h0[k - k0].y) << 16);
-              a8.y = e4m3x2_from_f16x2(h0[k - k0].z) | (e4m3x2_from_f16x2(h0[k - k0].w) << 16);
-              a8.z = e4m3x2_from_f16x2(h1[k - k0].x) | (e4m3x2_from_f16x2(h1[k - k0].y) << 16);
-              a8.w = e4m3x2_from_f16x2(h1[k - k0].z) | (e4m3x2_from_f16x2(h1[k - k0].w) << 16);
+              a8.x = e4m3x2_from_f16x2(h0[k].x) | (e4m3x2_from_f16x2(h0[k].y) << 16);
+              a8.y = e4m3x2_from_f16x2(h0[k].z) | (e4m3x2_from_f16x2(h0[k].w) << 16);
+              a8.z = e4m3x2_from_f16x2(h1[k].x) | (e4m3x2_from_f16x2(h1[k].y) << 16);
+              a8.w = e4m3x2_from_f16x2(h1[k].z) | (e4m3x2_from_f16x2(h1[k].w) << 16);
               sts128(E + p * 128u + ((qd ^ sw) << 4), a8);
             }
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < kConvTasks; ++k) {
-          if (k < kFull || tail) {
-            const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
-            sts128(E + p * 128u + (((4u + qd) ^ sw) << 4), lo[k]);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
@@ -566,11 +569,13 @@ cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_ro
   a.H = plan->H;
   a.W = plan->W;
   a.nimg = nimg;
-  a.band_rows = band_rows;
-  a.nbands = (plan->H + band_rows - 1) / band_rows;
+  (void)band_rows;
   a.npairs_x = (plan->W + 2 * roll::kStripW - 1) / (2 * roll::kStripW);
-  a.nunits = nimg * a.nbands * a.npairs_x;
-  const int nclusters = a.nunits < plan->num_sms / 2 ? a.nunits : plan->num_sms / 2;
+  a.total_rows = nimg * a.npairs_x * plan->H;
+  const int pairs = plan->num_sms / 2 > 0 ? plan->num_sms / 2 : 1;
+  a.rows_per_cluster = (a.total_rows + pairs - 1) / pairs;
+  if (a.rows_per_cluster < 8) a.rows_per_cluster = 8;                   // tiny launches: fewer pairs rather than halo-dominated bands
+  const int nclusters = (a.total_rows + a.rows_per_cluster - 1) / a.rows_per_cluster;
   if (derive) return launch_pdl(roll::conv_roll_d_kernel, 2 * nclusters, roll::kThreadsD, roll::kSmemBytesD, st, plan->map_row[in_buf], a);
   return launch_pdl(roll::conv_roll_kernel, 2 * nclusters, kThreads, roll::kSmemBytesR, st, plan->map_row[in_buf], a);
 }
