@@ -276,7 +276,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 constexpr int kConvWarps = 2;                             // 8 warps per CTA = 2 per scheduler: the register cap stays at 255 (10 warps: 168, spills)
 constexpr int kConvThreads = 32 * kConvWarps;
 constexpr int kThreadsD = kThreads + kConvThreads;
-constexpr int kConvTasks = (4 * kRowPix + kConvThreads - 1) / kConvThreads;   // 16-byte e4m3 chunks per thread and row (9)
 constexpr int kFD = 5, kED = 4;                           // F ring (fp16 rows, TMA) one deeper than the E ring (e4m3 rows, converters)
 constexpr uint32_t kOffED = kOffAR + kFD * kRowSlot, kOffBarD = kOffED + kED * kRowSlot;
 constexpr uint32_t kOffBiasD = kOffBarD + 256, kSmemBytesD = kOffBiasD + 256 + 1024;
@@ -313,11 +312,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < kFD; ++i) {
       mbar_init(bFullF + 8 * i, 1);         // this CTA's producer: arrive.expect_tx for its own row box
-      mbar_init(bEmptyF + 8 * i, 1 + kConvWarps);   // multicast commit of the fp16 MMAs + this CTA's converter warps
+      mbar_init(bEmptyF + 8 * i, 1 + 1);    // multicast commit of the fp16 MMAs + the converter warp that took the row
     }
     for (int i = 0; i < kED; ++i) {
       mbar_init(bEmptyE + 8 * i, 1);        // multicast commit of the e4m3 MMAs
-      mbar_init(bReady + 8 * i, 2 * kConvWarps);   // converter warps of both CTAs (used in CTA 0)
+      mbar_init(bReady + 8 * i, 2);         // one converter warp per CTA and row (used in CTA 0)
     }
     mbar_init(bW, 1);
     for (int i = 0; i < 4; ++i) {
@@ -433,79 +432,85 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
     }
   } else {
     // ------------------------------------------------------------ converters: build the e4m3 operand row of every stage
-    const int tc = (int)threadIdx.x - kThreads;                          // 0..kConvThreads-1
+    // The two converter warps take alternate rows (a whole row each), so each has two row periods for its fixed costs (barrier
+    // waits, proxy fence, load latency).  Task k < 16 of a lane: pixel group k (8 consecutive pixels of the row box),
+    // 16-channel quarter lane & 3; a quarter-warp (one 128-byte shared-memory transaction of the 16-byte accesses) covers the
+    // two pixels {i, i ^ 5} of the group: their swizzle phases differ in bit 0 (the two fp16 reads land in disjoint 16-byte
+    // columns) and in bit 2 (so do the two e4m3 writes) — no bank conflicts.  Task 16 (lanes 0..7): the pixels 128, 129.
     const size_t hw = (size_t)a.H * a.W;
     const uint32_t ready0 = two::map_to_cta(bReady, 0);
-    // Task k < 8 of this thread: pixel group g = kConvWarps k + (warp - 6) (8 consecutive pixels of the row box), 16-channel
-    // quarter lane & 3; a quarter-warp (one 128-byte shared-memory transaction of the 16-byte accesses) covers the two pixels
-    // {i, i ^ 5} of the group: their swizzle phases differ in bit 0 (the two fp16 reads land in disjoint 16-byte columns) and in
-    // bit 2 (so do the two e4m3 writes) — no bank conflicts.  Task 8 (threads 0..7): the two halo pixels 128, 129.
-    constexpr int kFull = kConvTasks - 1;                                // tasks that every thread has
-    const int tail = tc < 4 * kRowPix - kFull * kConvThreads;            // this thread has the last task too
+    const uint32_t mine = (uint32_t)(warp - 6);                          // rows with (j & 1) == mine
+    constexpr int kFull = kRowPix / 8;                                   // 16
+    constexpr int kTasks = kFull + 1;
+    const bool tail = lane < 4 * (kRowPix - 8 * kFull);                  // lanes 0..7
     const int pig = ((lane >> 2) & 1) ? ((lane >> 3) ^ 5) : (lane >> 3);
     const uint32_t qd = (uint32_t)lane & 3u;
-    auto task_px = [&](int k) { return k < kFull ? (kConvWarps * k + (warp - 6)) * 8 + pig : 128 + (tc >> 2); };
+    auto task_px = [&](int k) { return k < kFull ? k * 8 + pig : 8 * kFull + (lane >> 2); };
     pdl_wait_prior_grid();                                               // plain loads of the previous layer's output below
     uint32_t j = 0;
     BandWalk walk(a, cid);
     for (int img, px, yb, rb; walk.next(img, px, yb, rb);) {
       const int x0 = (px * 2 + (int)rank) * kStripW - 1;                 // image x of box pixel 0
       const uint8_t* p1 = reinterpret_cast<const uint8_t*>(a.in) + ((size_t)img * 2 + 1) * hw * 128 + 64 + qd * 16;
-      uint4 lo[kConvTasks];
+      uint4 lo[kTasks];
       auto fetch = [&](int s) {                                          // a_lo chunks of input row yb-1+s (zero outside the image)
         const int y = yb - 1 + s;
         const bool yok = y >= 0 && y < a.H;
 #pragma unroll
-        for (int k = 0; k < kConvTasks; ++k) {
+        for (int k = 0; k < kTasks; ++k) {
           const int x = x0 + task_px(k);
           const bool ok = yok && (k < kFull || tail) && x >= 0 && x < a.W;
           lo[k] = ok ? ldg128(p1 + ((size_t)y * a.W + x) * 128) : make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      fetch(0);
-      for (int s = 0; s < rb + 2; ++s, ++j) {
-        const uint32_t fs = j % kFD, fuse = j / kFD, es = j % kED, euse = j / kED;
+      int s = (int)((j ^ mine) & 1u);                                    // this warp's first row of the band
+      if (s < rb + 2) fetch(s);
+      for (; s < rb + 2; s += 2) {
+        const uint32_t jj = j + (uint32_t)s;
+        const uint32_t fs = jj % kFD, fuse = jj / kFD, es = jj % kED, euse = jj / kED;
         const uint32_t F = sF + fs * kRowSlot, E = sE + es * kRowSlot;
         mbar_wait(bFullF + 8 * fs, fuse & 1);                            // fp16 row landed
         mbar_wait(bEmptyE + 8 * es, (euse & 1) ^ 1);                     // e4m3 MMAs of the previous use are done
-        {
-          uint4 h0[kConvTasks], h1[kConvTasks];
 #pragma unroll
-          for (int k = 0; k < kConvTasks; ++k) {                         // all shared-memory reads of the row in flight at once
+        for (int k0 = 0; k0 < kTasks; k0 += 9) {                         // two batches: 18 / 16 shared-memory reads in flight
+          uint4 h0[9], h1[9];
+#pragma unroll
+          for (int k = k0; k < k0 + 9 && k < kTasks; ++k) {
             if (k < kFull || tail) {
               const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
-              h0[k] = lds128(F + p * 128u + (((2u * qd) ^ sw) << 4));
-              h1[k] = lds128(F + p * 128u + (((2u * qd + 1u) ^ sw) << 4));
+              h0[k - k0] = lds128(F + p * 128u + (((2u * qd) ^ sw) << 4));
+              h1[k - k0] = lds128(F + p * 128u + (((2u * qd + 1u) ^ sw) << 4));
             }
           }
 #pragma unroll
-          for (int k = 0; k < kConvTasks; ++k) {                         // a_lo half (loaded a row ago) while they return
-            if (k < kFull || tail) {
-              const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
-              sts128(E + p * 128u + (((4u + qd) ^ sw) << 4), lo[k]);
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < kConvTasks; ++k) {
+          for (int k = k0; k < k0 + 9 && k < kTasks; ++k) {
             if (k < kFull || tail) {
               const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
               uint4 a8;
-              a8.x = e4m3x2_from_f16x2(h0[k].x) | (e4m3x2_from_f16x2(h0[k].y) << 16);
-              a8.y = e4m3x2_from_f16x2(h0[k].z) | (e4m3x2_from_f16x2(h0[k].w) << 16);
-              a8.z = e4m3x2_from_f16x2(h1[k].x) | (e4m3x2_from_f16x2(h1[k].y) << 16);
-              a8.w = e4m3x2_from_f16x2(h1[k].z) | (e4m3x2_from_f16x2(h1[k].w) << 16);
+              a8.x = e4m3x2_from_f16x2(h0[k - k0].x) | (e4m3x2_from_f16x2(h0[k - k0].y) << 16);
+              a8.y = e4m3x2_from_f16x2(h0[k - k0].z) | (e4m3x2_from_f16x2(h0[k - k0].w) << 16);
+              a8.z = e4m3x2_from_f16x2(h1[k - k0].x) | (e4m3x2_from_f16x2(h1[k - k0].y) << 16);
+              a8.w = e4m3x2_from_f16x2(h1[k - k0].z) | (e4m3x2_from_f16x2(h1[k - k0].w) << 16);
               sts128(E + p * 128u + ((qd ^ sw) << 4), a8);
             }
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < kTasks; ++k) {                               // a_lo half (loaded while this warp's previous row was handled)
+          if (k < kFull || tail) {
+            const uint32_t p = (uint32_t)task_px(k), sw = p & 7u;
+            sts128(E + p * 128u + (((4u + qd) ^ sw) << 4), lo[k]);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA's reads
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bEmptyF + 8 * fs);                                 // this warp no longer reads F
+          mbar_arrive(bEmptyF + 8 * fs);                                 // F row no longer read by the converters
           two::mbar_arrive_cluster(ready0 + 8 * es);
         }
-        if (s + 1 < rb + 2) fetch(s + 1);                                // next row's a_lo: in flight while the barriers are awaited
+        if (s + 2 < rb + 2) fetch(s + 2);                                // this warp's next row (after the fence: it would wait for them)
       }
+      j += (uint32_t)(rb + 2);
     }
   }
   tc_fence_before();
