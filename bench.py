@@ -386,12 +386,15 @@ def main():
         chunk = min(B, a.chunk or max(1, (8 << 20) // (H * W)))
         n_mid_layers = weights.depth - 2
         # which body-layer kernel the library dispatches for this launch shape (pds_api.cu run_dncnn)
+        mid_bytes_px = 512.0                 # body layer: read + write [fp16 x 64 | e4m3(a) x 64 | e4m3(a_lo) x 64] per pixel
         if a.engine != "tcgen05":
             mid_kernel = "conv_mid_simt_kernel"
         elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0) > 0:
             hbm = bool(int(os.environ.get("PDS_TC_VARIANT", "0")) & 256)
             mid_kernel = ("roll::conv_roll_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand read from HBM)" if hbm else
                           "roll::conv_roll_d_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand rebuilt on chip from the fp16 row)")
+            if not hbm:                      # e4m3(a) neither stored nor read, except the store of the layer feeding the last one
+                mid_bytes_px = 384.0 + 64.0 / n_mid_layers
         else:
             mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
         total_flop = DNCNN_FLOP_PER_PX_MID_LAYER * float(B * H * W) * n_mid_layers * a.steps
@@ -425,7 +428,7 @@ def main():
                      iterations_per_call=a.e2e_iters, api="pds_restore_host (pinned host buffers in, pinned host buffer out)"),
             roofline=dict(bound="tensor", kernel=mid_kernel,
                           achieved=achieved, peak=pk["tensor"], unit="TFLOP/s", frac=(achieved / pk["tensor"]) if achieved else None,
-                          traffic=traffic, algorithmic_bytes_per_launch=512.0 * chunk * H * W,
+                          traffic=traffic, algorithmic_bytes_per_launch=mid_bytes_px * chunk * H * W,
                           issued_tflops_fp16_equiv=(2.0 * achieved) if (achieved and a.engine == "tcgen05") else None,
                           peak_source=pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                           launches=int(mid_n), avg_ms=mid_ms / max(1, mid_n),
@@ -434,7 +437,7 @@ def main():
                           note="algorithmic FLOPs = 73728 per pixel per layer (counted once).  Each algorithmic MAC is issued as one fp16 MAC "
                                "(a_hi*w_hi) plus two e4m3 MACs (a*w_lo + a_lo*w_hi, one K=128 kind::f8f6f4 MMA at twice the fp16 rate) = two "
                                "fp16-MAC times (issued_tflops_fp16_equiv), so frac <= 1/2 by construction; the board runs at its power cap (see clocks) "
-                               "and the layer also moves 512 B/pixel through HBM (profiles/: ~4.4 TB/s while the kernel runs)"),
+                               "and the layer also moves algorithmic_bytes_per_launch through HBM (profiles/: DRAM traffic and rate while the kernel runs)"),
             roofline_hbm=(dict(bound="hbm", kernel="dual_pw_kernel (fused Phi + over-relaxation + l2-ball/l1 terms + metrics), ours-B / random_sampling",
                                achieved=probe["dual"]["gbs"], peak=pk["hbm"], unit="GB/s", frac=probe["dual"]["gbs"] / pk["hbm"],
                                primal_achieved=probe["primal"]["gbs"], primal_frac=probe["primal"]["gbs"] / pk["hbm"],

@@ -17,7 +17,7 @@ $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "rc=$?"; wc -l gpurun_out/launches.csv
 echo "== ncu full: conv layers"
-ncu --set full --clock-control none --import-source on -k regex:"conv_roll_kernel|conv_first_tc_kernel|conv_last_tc_kernel" -s 60 -c 4 -o gpurun_out/prof_conv_layers -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_roll_d_kernel|conv_first_tc_kernel|conv_last_tc_kernel" -s 60 -c 4 -o gpurun_out/prof_conv_layers -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "rc=$?"
 echo "== ncu full: fused pointwise prox kernels (HBM evidence)"
 CMD2="python bench.py --steps 1 --warmup 3 --workload cfg2b --e2e-iters 1 --no-cpu-baseline --no-hbm-probe"
