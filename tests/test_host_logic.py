@@ -165,6 +165,37 @@ def test_ssim_restatement_matches_oracle_and_basic_properties():
     assert abs(eval_psnr(a, b) - O.eval_psnr(a, b)) < 1e-12
 
 
+def test_ssim_restatement_against_scipy_uniform_filter_formulation():
+    """scikit-image is absent (SSIM parity stays formally unpinned), but the primitive its structural_similarity is built on,
+    scipy.ndimage.uniform_filter, is here.  This spells out skimage 0.22's algorithm with it — per channel along axis 0
+    (channel_axis=0: a gray (H, W) image is H one-dimensional signals), size-7 uniform filter in 'reflect' mode, sample
+    covariance NP/(NP-1), K1=.01, K2=.03, crop (win-1)//2, float64 mean — and checks the product's valid-window form."""
+    from scipy.ndimage import uniform_filter
+    from pnp_pds_b200.utils.utils_eval import eval_ssim
+
+    def skimage_like(im1, im2):
+        data_range = im2.max() - im2.min()
+        vals = []
+        for ch in range(im1.shape[0]):
+            a, b = im1[ch].astype(np.float64), im2[ch].astype(np.float64)
+            NP = 7 ** a.ndim
+            cov = NP / (NP - 1)
+            ux, uy = uniform_filter(a, size=7), uniform_filter(b, size=7)
+            uxx, uyy, uxy = uniform_filter(a * a, size=7), uniform_filter(b * b, size=7), uniform_filter(a * b, size=7)
+            vx, vy, vxy = cov * (uxx - ux * ux), cov * (uyy - uy * uy), cov * (uxy - ux * uy)
+            C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+            S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+            S = S[tuple(slice(3, -3) for _ in range(a.ndim))]
+            vals.append(S.mean(dtype=np.float64))
+        return float(np.mean(vals))
+
+    rng = np.random.default_rng(5)
+    for shape in ((3, 40, 32), (24, 33), (3, 7, 9)):
+        a = rng.random(shape)
+        b = np.clip(a + 0.1 * rng.standard_normal(shape), 0, 1)
+        assert abs(eval_ssim(a, b) - skimage_like(a, b)) < 1e-10, shape
+
+
 def test_shard_range_partitions():
     from pnp_pds_b200.parallel import shard_range
     for n in (0, 1, 7, 256, 2560):
