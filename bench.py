@@ -46,6 +46,12 @@ WORKLOADS = {
     "cfg3": dict(method="ours-C", deg_op="blur", C=1, H=256, W=256, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
                  prm=dict(gamma1=0.0006, gamma2=1 / 0.0006, alpha_n=0.9, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.0, sp_nl=0.0,
                           poisson_alpha=100, r=1.0), poisson=True),
+    # BASELINE configs[4]: hyper-parameter grid search over 256 gray 256x256 images sharded over 8 GPUs = 32 images per GPU,
+    # here x 8 grid points (alpha_n = 0.82 ... 0.96, main.py:142-153) as ONE mixed batch of 256 items with per-item parameters
+    "cfg5": dict(method="ours-A", deg_op="blur", C=1, H=256, W=256, batch=256, arch="DnCNN_nobn_nch_1_nlev_0.01",
+                 prm=dict(gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.0,
+                          poisson_alpha=300, r=1.0), poisson=False,
+                 grid=[dict(alpha_n=0.82 + 0.02 * g) for g in range(8)]),
 }
 DNCNN_FLOP_PER_PX_MID_LAYER = 2 * 9 * 64 * 64          # one 64->64 3x3 layer (18 of these per denoiser call)
 
@@ -301,10 +307,12 @@ def main():
     shape = (B, C, H, W)
     pin = lambda: torch.empty(shape, dtype=torch.float32, pin_memory=True)
     h_true, h_x0, h_obs, h_out = pin(), pin(), pin(), pin()
+    n_grid = len(wl.get("grid") or [None])          # item b = (image b // n_grid, grid point b % n_grid)
     for b in range(B):
-        h_true[b] = torch.from_numpy(np.asarray(trues[b % n_distinct], dtype=np.float32).reshape(C, H, W))
-        h_x0[b] = torch.from_numpy(np.asarray(x0s[b % n_distinct], dtype=np.float32).reshape(C, H, W))
-        h_obs[b] = torch.from_numpy(np.asarray(obss[b % n_distinct], dtype=np.float32).reshape(C, H, W))
+        i = (b // n_grid) % n_distinct
+        h_true[b] = torch.from_numpy(np.asarray(trues[i], dtype=np.float32).reshape(C, H, W))
+        h_x0[b] = torch.from_numpy(np.asarray(x0s[i], dtype=np.float32).reshape(C, H, W))
+        h_obs[b] = torch.from_numpy(np.asarray(obss[i], dtype=np.float32).reshape(C, H, W))
 
     max_iter = a.warmup + 2 * a.steps + 2 * a.e2e_iters + 4
     eng = Engine(B, C, H, W, method=mid, deg_op=wl["deg_op"], max_iter=max_iter, conv_engine=a.engine, device=local_rank,
@@ -313,8 +321,14 @@ def main():
         eng.set_blur_kernel(hker)
     elif wl["deg_op"] == "random_sampling":
         eng.set_mask(operators.sampling_mask(H, W, prm["r"]))
-    eng.set_params(item_params(mid, n, prm["gamma1"], prm["gamma2"], prm["alpha_s"], prm["alpha_n"], prm["myLambda"], prm["gaussian_nl"],
-                               prm["sp_nl"], prm["poisson_alpha"], prm["r"]))
+    def params_for(q):
+        return item_params(mid, n, q["gamma1"], q["gamma2"], q["alpha_s"], q["alpha_n"], q["myLambda"], q["gaussian_nl"], q["sp_nl"],
+                           q["poisson_alpha"], q["r"])
+    grid = wl.get("grid")
+    if grid:        # one batch mixes the grid points
+        eng.set_params([params_for({**prm, **grid[b % len(grid)]}) for b in range(B)])
+    else:
+        eng.set_params(params_for(prm))
     eng.load_dncnn(weights)
 
     # ---- device-resident timing: inputs already in HBM when the timed region starts

@@ -8,7 +8,7 @@ echo "== pytest -m gpu"; timeout 1500 python -m pytest tests/ -x -q -m gpu > gpu
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/BENCH_ref.json 2> gpurun_out/BENCH_ref.err; tail -c 300 gpurun_out/BENCH_ref.json
 echo "== bench default"; timeout 900 python bench.py > gpurun_out/BENCH_default.json 2> gpurun_out/BENCH_default.err; echo "rc=$?"; tail -c 400 gpurun_out/BENCH_default.json; tail -3 gpurun_out/BENCH_default.err
-for w in cfg1 cfg2 cfg3 cfg2b; do
+for w in cfg1 cfg2 cfg3 cfg2b cfg5; do
   timeout 600 python bench.py --workload $w --steps 20 --warmup 5 --e2e-iters 100 --no-hbm-probe > gpurun_out/BENCH_$w.json 2> gpurun_out/BENCH_$w.err; echo "$w rc=$?"
 done
 CMD="python bench.py --steps 2 --warmup 3 --workload cfg4 --batch 8 --e2e-iters 1 --no-cpu-baseline --no-hbm-probe"

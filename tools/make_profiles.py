@@ -58,7 +58,7 @@ def summarize(rep, tag, out_name):
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
-    for name in ("default", "cfg1", "cfg2", "cfg3", "cfg2b"):
+    for name in ("default", "cfg1", "cfg2", "cfg3", "cfg2b", "cfg5"):
         p = os.path.join(SRC, f"BENCH_{name}.json")
         if os.path.exists(p):
             shutil.copy(p, os.path.join(OUT, f"{tag}_bench_{name}.json"))
