@@ -266,7 +266,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 //     purpose, as for the TMEM-drained signal: a release at cluster scope compiles to MEMBAR.ALL.GPU per warp and row, and
 //     the writes it would order are already performed (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC of the proxy fence);
 //   * two converter warps, not four: with 8 warps per CTA every scheduler holds two and the register cap stays at 255; with
-//     10 warps it drops to 168, ptxas spills in the MMA-issue loop and the tensor pipe starves (measured: 1.43 vs 1.12 ms);
+//     10 warps it drops to 168, ptxas spills in the MMA-issue loop and the tensor pipe starves (measured: 1.43 vs 1.12 ms).
+//     The two warps take alternate rows (a whole row each): splitting every row between them made the per-row fixed costs
+//     (barrier waits, proxy fence, load latency) the pacing stage;
 //   * the F ring (5 slots) is one deeper than the E ring (4), so the row loads run ahead of the converters;
 //   * the MMA issuer waits for "ready" only (it implies that both F rows have landed), and frees F and E separately;
 //   * the layers feeding this kernel skip the e4m3(a) store (write_a8 = 0): 384 instead of 512 HBM bytes per pixel and layer.
@@ -536,9 +538,11 @@ int roll_setup() {
   return 0;
 }
 
-// Rows per band, or 0 when the tile kernels are the better choice for this launch.  Cost model in units of "one 128-pixel row
-// step of a CTA pair": a band of rb rows costs rb + 2 steps (two halo rows), the launch costs ceil(units / pairs) bands per
-// pair; the 2-CTA tile kernel needs ~1.2 steps per tile pair (it re-reads the A operand: 3246 vs 2912 cycles per 128
+// Dispatch decision: > 0 when the row-streaming kernels are the better choice for this launch, 0 for the tile kernels.  (The
+// value is the band height of the fixed-band estimate; the launch itself splits the rows evenly over the CTA pairs, BandWalk,
+// which never costs more steps.)  Cost model in units of "one 128-pixel row step of a CTA pair": a band of rb rows costs
+// rb + 2 steps (two halo rows), the launch costs ceil(units / pairs) bands per pair; the 2-CTA tile kernel needs ~1.2 steps
+// per tile pair (it re-reads the A operand: 3246 vs 2912 cycles per 128
 // pixels in ncu, and it re-fetches halos; calibrated on single 512x512 and 1024x1024 images).
 // `force`: ignore the comparison with the tile kernels (tests).
 int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
