@@ -538,31 +538,29 @@ int roll_setup() {
   return 0;
 }
 
-// Dispatch decision: > 0 when the row-streaming kernels are the better choice for this launch, 0 for the tile kernels.  (The
-// value is the band height of the fixed-band estimate; the launch itself splits the rows evenly over the CTA pairs, BandWalk,
-// which never costs more steps.)  Cost model in units of "one 128-pixel row step of a CTA pair": a band of rb rows costs
-// rb + 2 steps (two halo rows), the launch costs ceil(units / pairs) bands per pair; the 2-CTA tile kernel needs ~1.2 steps
-// per tile pair (it re-reads the A operand: 3246 vs 2912 cycles per 128
-// pixels in ncu, and it re-fetches halos; calibrated on single 512x512 and 1024x1024 images).
-// `force`: ignore the comparison with the tile kernels (tests).
-int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
-  if (W % roll::kStripW != 0 || H < 8 || nimg < 1) return 0;
+// Dispatch decision: rows per CTA pair (> 0) when the row-streaming kernels are the better choice for this launch, 0 for the
+// tile kernels.  Cost model in units of "one row step of a CTA pair" (2 x 128 pixels): the launch splits the rows of all
+// (image, strip pair) columns evenly over the pairs (BandWalk), a pair pays its rows plus two halo rows per band; strips that
+// hang over the right image edge (width not a multiple of 256) are paid in full.  The 2-CTA tile kernel needs ~1.2 steps per
+// tile pair (it re-reads the A operand: 3246 vs 2912 cycles per 128 pixels in ncu, and it re-fetches halos; calibrated on
+// single 512x512 and 1024x1024 images).  `force`: ignore the comparison with the tile kernels (tests).
+int roll_rows_per_pair(int nimg, int H, int W, int num_sms) {
   const long long npx = (W + 2 * roll::kStripW - 1) / (2 * roll::kStripW);
   const long long pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
-  long long best_cost = -1;
-  int best_rb = 0;
-  for (int rb = 8; rb <= 64; ++rb) {
-    const long long units = (long long)nimg * ((H + rb - 1) / rb) * npx;
-    const long long cost = ((units + pairs - 1) / pairs) * (rb + 2);
-    if (best_cost < 0 || cost <= best_cost) {
-      best_cost = cost;
-      best_rb = rb;
-    }
-  }
-  if (force) return best_rb;
+  const long long total = (long long)nimg * npx * H;
+  const long long rpc = (total + pairs - 1) / pairs;
+  return (int)(rpc < 8 ? 8 : rpc);                                      // tiny launches: fewer pairs rather than halo-dominated bands
+}
+int roll_band_rows(int nimg, int H, int W, int num_sms, bool force) {
+  if (W < roll::kStripW || H < 8 || nimg < 1) return 0;
+  const long long pairs = num_sms / 2 > 0 ? num_sms / 2 : 1;
+  const int rpc = roll_rows_per_pair(nimg, H, W, num_sms);
+  if (force) return rpc;
+  const double bands = 1.0 + (double)rpc / (double)H;                   // columns a pair's share touches, on average
+  const double roll_cost = (double)rpc + 2.0 * bands;
   const long long tile_pairs = ((long long)nimg * ((H + kTileRows - 1) / kTileRows) * ((W + kTileCols - 1) / kTileCols) + 1) / 2;
   const double tile_cost = 1.2 * (double)((tile_pairs + pairs - 1) / pairs);
-  return (double)best_cost < tile_cost ? best_rb : 0;
+  return roll_cost < tile_cost ? rpc : 0;
 }
 
 cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_rows, const DncnnLayerW& L, float slope, int derive,
@@ -578,12 +576,9 @@ cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_ro
   a.H = plan->H;
   a.W = plan->W;
   a.nimg = nimg;
-  (void)band_rows;
   a.npairs_x = (plan->W + 2 * roll::kStripW - 1) / (2 * roll::kStripW);
   a.total_rows = nimg * a.npairs_x * plan->H;
-  const int pairs = plan->num_sms / 2 > 0 ? plan->num_sms / 2 : 1;
-  a.rows_per_cluster = (a.total_rows + pairs - 1) / pairs;
-  if (a.rows_per_cluster < 8) a.rows_per_cluster = 8;                   // tiny launches: fewer pairs rather than halo-dominated bands
+  a.rows_per_cluster = band_rows > 0 ? band_rows : roll_rows_per_pair(nimg, plan->H, plan->W, plan->num_sms);
   const int nclusters = (a.total_rows + a.rows_per_cluster - 1) / a.rows_per_cluster;
   if (derive) return launch_pdl(roll::conv_roll_d_kernel, 2 * nclusters, roll::kThreadsD, roll::kSmemBytesD, st, plan->map_row[in_buf], a);
   return launch_pdl(roll::conv_roll_kernel, 2 * nclusters, kThreads, roll::kSmemBytesR, st, plan->map_row[in_buf], a);

@@ -104,17 +104,19 @@ def test_full_size_linearity_free_checks():
     assert a.min() >= 0 and a.max() <= 1
 
 
-@pytest.mark.parametrize("shape", [(12, 1, 256, 256), (24, 3, 120, 128), (16, 1, 72, 384), (1, 1, 23, 128), (2, 3, 9, 256)])
+@pytest.mark.parametrize("shape", [(12, 1, 256, 256), (24, 3, 120, 128), (16, 1, 72, 384), (1, 1, 23, 128), (2, 3, 9, 256),
+                                   (2, 1, 40, 321), (3, 3, 19, 200), (1, 1, 64, 130)])
 def test_row_streaming_body_kernel_matches_tile_kernels(shape):
     """Large launches whose width splits into 128-pixel strips run the row-streaming body kernel (dncnn_roll.cu):
     same operands and the same MMA order per output element, so the results are bit-identical.  Covers partial last bands,
-    a lone strip whose pair partner lies outside the image (W = 128) and an odd strip count (W = 384)."""
+    a lone strip whose pair partner lies outside the image (W = 128), an odd strip count (W = 384) and widths that are not
+    a multiple of the strip width (the last strip hangs over the right edge: TMA zero-fill in, masked stores out)."""
     from pnp_pds_b200 import _lib
     from pnp_pds_b200.engine import Engine
     from pnp_pds_b200.models.weights import load_weights
     B, C, H, W = shape
     lib = _lib.load()
-    assert lib.pds_debug_roll_band_rows(B, H, W, 1) > 0, "width is not a multiple of 128"
+    assert lib.pds_debug_roll_band_rows(B, H, W, 1) > 0, "narrower than one strip"
     w = load_weights(weights_path(SIMPLE[1] if C == 3 else SIMPLE[0]))
     x = np.random.default_rng(11).random(shape).astype(np.float32)
     outs = {}

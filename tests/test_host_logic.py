@@ -241,16 +241,18 @@ def test_gather_rows_gloo_world_size_2(tmp_path):
 
 
 def test_row_streaming_band_selection_cost_model():
-    """pds_debug_roll_band_rows is host arithmetic (148 SMs assumed without a device): row streaming for large launches
-    whose width splits into 128-pixel strips, tile kernels otherwise."""
+    """pds_debug_roll_band_rows is host arithmetic (148 SMs assumed without a device): rows per CTA pair when the
+    row-streaming kernels serve the launch (large launches at least one 128-pixel strip wide), 0 for the tile kernels."""
     from pnp_pds_b200 import _lib
     lib = _lib.load()
     f = lib.pds_debug_roll_band_rows
-    assert f(8, 1024, 1024, 0) == 64                      # cfg4: 8 images per denoiser pass
-    assert 8 <= f(1, 1024, 1024, 0) <= 64                 # one 3x1024x1024 image still fills the CTA pairs
-    assert f(1, 256, 256, 0) == 0                         # a single small image: too few bands, tiles win
-    assert f(1, 512, 512, 0) == 14                        # 37 bands x 2 strip pairs = one band per CTA pair
-    assert f(1, 100, 100, 0) == 0 and f(1, 100, 100, 1) == 0      # width not a multiple of 128: never
+    assert f(8, 1024, 1024, 0) == 443                     # cfg4: 8 images per denoiser pass, 32768 strip-pair rows over 74 pairs
+    assert f(1, 1024, 1024, 0) == 56                      # one 1024x1024 image still fills the CTA pairs
+    assert f(1, 256, 256, 0) == 0                         # a single small image: halo rows dominate, tiles win
+    assert f(1, 512, 512, 0) == 14                        # 1024 strip-pair rows over 74 pairs
+    assert f(1, 100, 100, 0) == 0 and f(1, 100, 100, 1) == 0      # narrower than one strip: never
+    assert f(16, 321, 481, 0) > 0                         # ragged widths: 481 = 3.76 strips, still cheaper than tiles
+    assert f(16, 200, 130, 0) == 0                        # ... but not when most of a strip pair hangs over the edge
     assert f(1, 256, 256, 1) >= 8                         # forced (tests)
 
 
