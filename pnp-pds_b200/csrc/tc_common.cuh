@@ -172,11 +172,12 @@ __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, 
       l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
     }
     st_global_256(dst_p0 + c0 + q * 16, hi);
+    if (write_a8) {                          // warp-uniform
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      a8[q * 4 + k] = e4m3x2_from_f16x2(hi[2 * k]) | (e4m3x2_from_f16x2(hi[2 * k + 1]) << 16);
-      l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+      for (int k = 0; k < 4; ++k) a8[q * 4 + k] = e4m3x2_from_f16x2(hi[2 * k]) | (e4m3x2_from_f16x2(hi[2 * k + 1]) << 16);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
   }
   if (write_a8) st_global_256(dst_p1 + c0, a8);
   st_global_256(dst_p1 + 64 + c0, l8);
