@@ -256,6 +256,67 @@ def test_row_streaming_band_selection_cost_model():
     assert f(1, 256, 256, 1) >= 8                         # forced (tests)
 
 
+def test_converter_lane_mapping_is_complete_and_conflict_free():
+    """Host restatement of the lane -> (pixel, 16-channel quarter) mapping of the converter warps in conv_roll_d_kernel
+    (dncnn_roll.cu): every 16-byte chunk of the 130-pixel row box is produced exactly once, and within a quarter-warp (the
+    unit in which 16-byte shared-memory accesses are served) the two fp16 reads and the two e4m3 writes of SWIZZLE_128B rows
+    land in eight distinct 16-byte columns, i.e. all 32 banks once."""
+    row_pix, full = 130, 16
+    seen = set()
+    for k in range(full + 1):
+        for lane in range(32):
+            if k == full and lane >= 4 * (row_pix - 8 * full):
+                continue
+            pig = ((lane >> 3) ^ 5) if ((lane >> 2) & 1) else (lane >> 3)
+            p = k * 8 + pig if k < full else 8 * full + (lane >> 2)
+            qd = lane & 3
+            assert 0 <= p < row_pix and (p, qd) not in seen
+            seen.add((p, qd))
+        if k == full:
+            break
+        for q in range(4):                                 # quarter-warps of task k
+            cols = {"ld0": [], "ld1": [], "st_a8": [], "st_lo": []}
+            for lane in range(8 * q, 8 * q + 8):
+                pig = ((lane >> 3) ^ 5) if ((lane >> 2) & 1) else (lane >> 3)
+                p, qd = k * 8 + pig, lane & 3
+                sw = p & 7
+                cols["ld0"].append((2 * qd) ^ sw)
+                cols["ld1"].append((2 * qd + 1) ^ sw)
+                cols["st_a8"].append(qd ^ sw)
+                cols["st_lo"].append((4 + qd) ^ sw)
+            for name, c in cols.items():
+                assert sorted(c) == list(range(8)), (k, q, name, c)
+    assert len(seen) == 4 * row_pix
+
+
+def test_band_walk_covers_every_row_once():
+    """Host restatement of BandWalk + launch_conv_mid_roll (dncnn_roll.cu): the CTA pairs' contiguous shares, cut into bands at
+    the column boundaries, cover every (image, strip pair, row) exactly once and differ by at most one share in length."""
+    from pnp_pds_b200 import _lib
+    f = _lib.load().pds_debug_roll_band_rows
+    for nimg, H, W in ((8, 1024, 1024), (1, 512, 512), (12, 256, 256), (16, 321, 481), (1, 23, 128), (2, 9, 256)):
+        rpc = f(nimg, H, W, 1)
+        npx = (W + 255) // 256
+        total = nimg * npx * H
+        assert rpc == max(8, -(-total // 74))
+        nclusters = -(-total // rpc)
+        assert nclusters <= 74
+        seen = np.zeros((nimg, npx, H), dtype=np.int32)
+        steps = []
+        for cid in range(nclusters):
+            g, end, n = cid * rpc, min(total, (cid + 1) * rpc), 0
+            while g < end:
+                col, yb = divmod(g, H)
+                rb = min(H - yb, end - g)
+                img, px = divmod(col, npx)
+                seen[img, px, yb:yb + rb] += 1
+                g += rb
+                n += rb + 2
+            steps.append(n)
+        assert (seen == 1).all()
+        assert max(steps) <= rpc + 2 * (2 + rpc // H)
+
+
 def test_summary_textfile_matches_reference_format(tmp_path):
     """utils_textfile against strings produced by the reference's writer (tests/golden/textfile.json, recorded here)."""
     import json
