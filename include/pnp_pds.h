@@ -165,10 +165,11 @@ size_t pds_workspace_bytes(pds_handle_t h);
 
 /* ---- test hooks (hardware probes used by tests/test_gpu_tcgen05.py; not part of the drop-in surface) ---- */
 /* kernel-selection switches of the tcgen05 engine: bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel for the body layers,
- * bit 6 forces the row-streaming body kernel (dncnn_roll.cu) wherever the width is a multiple of 128, bit 7 disables it */
+ * bit 6 forces the row-streaming body kernels (dncnn_roll.cu) wherever the image is at least 128 pixels wide, bit 7 disables
+ * them, bit 8 makes them read the e4m3(a) operand from HBM instead of rebuilding it on chip (every layer then stores it) */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant);
-/* rows per band the row-streaming body kernel would use for a launch of nimg images of H x W on the current device;
- * 0 = the tile kernels run instead (width not a multiple of 128, or the cost model prefers tiles; force != 0 skips that comparison) */
+/* rows per CTA pair when the row-streaming body kernels serve a launch of nimg images of H x W on the current device;
+ * 0 = the tile kernels run instead (narrower than 128 pixels, or the cost model prefers tiles; force != 0 skips that comparison) */
 int pds_debug_roll_band_rows(int nimg, int H, int W, int force);
 /* one tcgen05.mma (M=128, N=16, K=16, B = identity) over a shared-memory region whose 16-byte chunk c
  * holds (c & 1023, c >> 10) repeated; out_host[128][16] therefore reveals which chunk fed every (row, k) */
