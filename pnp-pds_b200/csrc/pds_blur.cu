@@ -139,9 +139,11 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(BlurArgs a) {
 // window with LDS.128 (pitch = 4 mod 32 floats: conflict-free) and applies up to (2 RX + 1) x 16 FMAs whose weight operand
 // comes straight from the kernel-parameter constant bank (no load, no register); all-zero taps are skipped by a uniform
 // branch on that constant.  24 FMAs per shared-memory load instruction: the stencil runs on the FP32 pipe, not on the LSU.
-template <int MODE, int METHOD, int RY, int RX>
+// OX = outputs per thread along x: 16 for launches that fill the GPU (128 x 32 tiles), 4 for small ones (32 x 32 tiles: a single
+// 256 x 256 image is 64 blocks instead of 16, and a thread's serial work — what bounds a launch that small — is a quarter).
+template <int MODE, int METHOD, int RY, int RX, int OX>
 __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__ BlurArgs a) {
-  constexpr int OX = 16, TWR = 8 * OX, THR = 32;
+  constexpr int TWR = 8 * OX, THR = 32;
   constexpr int HC = TWR + 2 * RX, HR = THR + 2 * RY;
   constexpr int PITCH = ((HC + 27) / 32) * 32 + 4;
   constexpr int NV = OX + 2 * RX, NV4 = (NV + 3) / 4;
@@ -288,10 +290,37 @@ __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__
   }
 }
 
-template <int RY, int RX>
+template <int RY, int RX, int OX>
 constexpr size_t rt_smem_bytes() {
-  constexpr int HC = 128 + 2 * RX, HR = 32 + 2 * RY, PITCH = ((HC + 27) / 32) * 32 + 4;
+  constexpr int HC = 8 * OX + 2 * RX, HR = 32 + 2 * RY, PITCH = ((HC + 27) / 32) * 32 + 4;
   return (size_t)(HR * PITCH) * sizeof(float);
+}
+
+template <int MODE, int METHOD, int RY, int RX, int OX>
+cudaError_t launch_rt_ox(const BlurArgs& a0, const Dims& d, cudaStream_t st) {
+  BlurArgs a = a0;
+  a.tiles_x = (d.W + 8 * OX - 1) / (8 * OX);
+  const int tiles_y = (d.H + 31) / 32;
+  dim3 grid(a.tiles_x * tiles_y, d.B * d.C);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(blur_rt_kernel<MODE, METHOD, RY, RX, OX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)rt_smem_bytes<RY, RX, OX>());
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  blur_rt_kernel<MODE, METHOD, RY, RX, OX><<<grid, 256, rt_smem_bytes<RY, RX, OX>(), st>>>(a);
+  return cudaGetLastError();
+}
+
+inline int blur_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n = v;
+  }
+  return n;
 }
 
 template <int MODE, int METHOD, int RY, int RX>
@@ -305,17 +334,10 @@ cudaError_t launch_rt(BlurArgs& a, const Dims& d, const BlurTaps& t, int which, 
   for (int i = 0; i < (2 * RY + 1) * (2 * RX + 1); ++i) a.wbox[i] = 0.f;
   for (int k = 0; k < t.ntaps; ++k)
     a.wbox[((int)t.off_host[which][k].x + RY) * (2 * RX + 1) + (int)t.off_host[which][k].y + RX] = t.w_host[k];
-  a.tiles_x = (d.W + 127) / 128;
-  const int tiles_y = (d.H + 31) / 32;
-  dim3 grid(a.tiles_x * tiles_y, d.B * d.C);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(blur_rt_kernel<MODE, METHOD, RY, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rt_smem_bytes<RY, RX>());
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  blur_rt_kernel<MODE, METHOD, RY, RX><<<grid, 256, rt_smem_bytes<RY, RX>(), st>>>(a);
-  return cudaGetLastError();
+  // 128 x 32 tiles when they give every SM two blocks, 32 x 32 tiles otherwise
+  const long long blocks16 = (long long)((d.W + 127) / 128) * ((d.H + 31) / 32) * d.B * d.C;
+  if (blocks16 >= 2LL * blur_num_sms()) return launch_rt_ox<MODE, METHOD, RY, RX, 16>(a, d, st);
+  return launch_rt_ox<MODE, METHOD, RY, RX, 4>(a, d, st);
 }
 
 size_t smem_bytes(const BlurTaps& t) {
