@@ -46,11 +46,12 @@ WORKLOADS = {
     "cfg3": dict(method="ours-C", deg_op="blur", C=1, H=256, W=256, batch=1, arch="DnCNN_nobn_nch_1_nlev_0.01",
                  prm=dict(gamma1=0.0006, gamma2=1 / 0.0006, alpha_n=0.9, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.0, sp_nl=0.0,
                           poisson_alpha=100, r=1.0), poisson=True),
-    # BASELINE configs[4]: hyper-parameter grid search over 256 gray 256x256 images sharded over 8 GPUs = 32 images per GPU,
-    # here x 8 grid points (alpha_n = 0.82 ... 0.96, main.py:142-153) as ONE mixed batch of 256 items with per-item parameters
-    "cfg5": dict(method="ours-A", deg_op="blur", C=1, H=256, W=256, batch=256, arch="DnCNN_nobn_nch_1_nlev_0.01",
+    # BASELINE configs[4]: hyper-parameter grid search over 256 gray 256x256 images x 8 grid points (alpha_n = 0.82 ... 0.96,
+    # main.py:142-153) = 2048 work items, FIXED total, sharded over the ranks (strong scaling) through main.grid_search:
+    # batches mix grid points (per-item parameters), the final [PSNR, SSIM, c] rows are all-gathered over NCCL.
+    "cfg5": dict(method="ours-A", deg_op="blur", C=1, H=256, W=256, batch=256, images=256, arch="DnCNN_nobn_nch_1_nlev_0.01",
                  prm=dict(gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, myLambda=1.0, gaussian_nl=0.01, sp_nl=0.0,
-                          poisson_alpha=300, r=1.0), poisson=False,
+                          poisson_alpha=300, r=1.0), poisson=False, strong=True,
                  grid=[dict(alpha_n=0.82 + 0.02 * g) for g in range(8)]),
 }
 DNCNN_FLOP_PER_PX_MID_LAYER = 2 * 9 * 64 * 64          # one 64->64 3x3 layer (18 of these per denoiser call)
@@ -137,7 +138,7 @@ def cpu_iteration_setup(wl, H, W):
     x0, obs = O.synthesize_observation(img, wl["deg_op"], h, prm["r"], prm["gaussian_nl"], prm["sp_nl"], wl["poisson"],
                                        prm["poisson_alpha"])
     den = lambda z: O.dncnn_forward_torch(w.layers, z, w.slope, w.residual_sign, w.clamp)
-    state = dict(x=x0, y=np.zeros(x0.shape), s=np.zeros(x0.shape))
+    state = dict(x=x0, y=np.zeros(x0.shape), s=np.zeros(x0.shape), iters=0, psnr=None, x0=x0, obs=obs, img=img)
     method = O.METHOD_ALIASES.get(wl["method"], wl["method"])
 
     def one_iteration():
@@ -147,8 +148,11 @@ def cpu_iteration_setup(wl, H, W):
                                                 prm["alpha_n"], prm["myLambda"], prm["gaussian_nl"], prm["sp_nl"], prm["poisson_alpha"],
                                                 1, method, prm["r"], snapshots=(1,), y0=st["y"], s0=st["s"])
         st["x"], st["y"], st["s"] = snaps[1]["x"], snaps[1]["y"], snaps[1]["s"]
-        return float(psnr[-1])
+        st["iters"] += 1
+        st["psnr"] = float(psnr[-1])
+        return st["psnr"]
 
+    one_iteration.state = state
     return one_iteration
 
 
@@ -177,7 +181,25 @@ def cpu_baseline(wl, budget_s=25.0):
     return dict(value=size[0] * size[1] / dt / 1e6, unit=UNIT, cores=torch.get_num_threads(), kind="port",
                 sample=f"1 image {wl['C']}x{size[0]}x{size[1]} of the workload, {n} timed iteration(s) after 1 warm-up, "
                        f"oracle port (numpy FFT blur + torch CPU conv2d, {torch.get_num_threads()} threads), "
-                       f"os.cpu_count()={os.cpu_count()}")
+                       f"os.cpu_count()={os.cpu_count()}"), it.state
+
+
+def parity_against_cpu_leg(wl, st, weights, hker):
+    """The CPU leg's iterate is not thrown away: the same image, observation and iteration count go through the product
+    (iteration.run_batch -> pds_restore_host) and the line reports how far the two final iterates are apart — the
+    north-star gates are rel. L2 <= 1e-4 and |dPSNR| <= 0.01 dB (at the full iteration count; tests/ hold those runs)."""
+    from pnp_pds_b200 import iteration, operators
+    prm = wl["prm"]
+    phi, adj = operators.get_observation_operators(wl["deg_op"], hker, prm["r"])
+    n_it = int(st["iters"])
+    res = iteration.run_batch(np.asarray(st["x0"])[None], np.asarray(st["obs"])[None], np.asarray(st["img"])[None], phi, adj, prm, weights,
+                              n_it, wl["method"], wl["C"], ssim="none")
+    xg = res["x"][0].astype(np.float64).ravel()
+    xc = np.asarray(st["x"], dtype=np.float64).ravel()
+    return dict(rel_l2=float(np.linalg.norm(xg - xc) / np.linalg.norm(xc)), dpsnr_db=float(abs(res["psnr"][-1, 0] - st["psnr"])),
+                psnr_gpu=float(res["psnr"][-1, 0]), psnr_cpu=float(st["psnr"]), iterations=n_it, shape=list(np.shape(st["img"])),
+                against="the cpu_baseline leg's own final iterate (oracle port, float64 state + fp32 conv2d), same x_0 / x_obsrv",
+                gates=dict(rel_l2=1e-4, dpsnr_db=0.01))
 
 
 def hbm_probe(device_index, engine):
@@ -267,6 +289,8 @@ def main():
     ap.add_argument("--e2e-iters", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hbm-probe", action="store_true")
+    ap.add_argument("--tc-variant", type=int, default=0, help="kernel-selection test hook (pds_debug_set_tc_variant)")
+    ap.add_argument("--images", type=int, default=0, help="cfg5: number of images (default 256)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     wl = dict(WORKLOADS[a.workload])
@@ -281,38 +305,51 @@ def main():
     from pnp_pds_b200.engine import RESIDENT_METHODS, Engine, canonical_method, metrics_from_traces
     from pnp_pds_b200.iteration import item_params
     from pnp_pds_b200.models.weights import load_weights
-    from pnp_pds_b200.parallel import gather_rows, init_distributed
+    from pnp_pds_b200.parallel import gather_rows, init_distributed, shard_range
 
     rank, local_rank, world = init_distributed()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    B, C, H, W = wl["batch"], wl["C"], wl["H"], wl["W"]
+    C, H, W = wl["C"], wl["H"], wl["W"]
     n = C * H * W
     prm = wl["prm"]
     mid = RESIDENT_METHODS[canonical_method(wl["method"])]
     hker = load_assets()
     weights = load_weights(os.path.join(GOLDEN, "weights", wl["arch"] + ".pdsw"))
+    strong = bool(wl.get("strong"))
+    n_grid = len(wl.get("grid") or [None])
+    if strong:          # fixed total work: items = images x grid points, contiguous block per rank (parallel.shard_range)
+        n_images = a.images or wl["images"]
+        n_items = n_images * n_grid
+        lo, hi = shard_range(n_items, rank, world)
+        B = hi - lo
+        item_image = [(lo + b) // n_grid for b in range(B)]
+        item_grid = [(lo + b) % n_grid for b in range(B)]
+    else:               # fixed work per rank: item b = (image b // n_grid, grid point b % n_grid)
+        B = wl["batch"]
+        n_items = B * world
+        item_image = [rank * 1000 + (b // n_grid) % min(B, 8) for b in range(B)]
+        item_grid = [b % n_grid for b in range(B)]
 
-    # ---- synthetic inputs (host, pinned).  8 distinct images, repeated to the batch; the observation is
-    # synthesised with the product's own operator + the reference-order noise functions (seed 1234).
+    # ---- synthetic inputs (host, pinned).  Weak workloads: 8 distinct images per rank repeated to the batch; cfg5: one image
+    # per image index.  The observation is synthesised with the product's own operator + the reference-order noise
+    # functions (seed 1234).
     phi, adj = operators.get_observation_operators(wl["deg_op"], hker, prm["r"])
-    n_distinct = min(B, 8)
-    trues, x0s, obss = [], [], []
-    for b in range(n_distinct):
-        img = synthetic_image(rank * 1000 + b, C, H, W)
+    synth = {}
+    for i in sorted(set(item_image)):
+        img = synthetic_image(i, C, H, W)
         x0, obs = pmain.synthesize_observation(img, phi, wl["deg_op"], prm["gaussian_nl"], prm["sp_nl"], wl["poisson"], prm["poisson_alpha"])
-        trues.append(img); x0s.append(x0); obss.append(obs)
+        synth[i] = (img, x0, obs)
     shape = (B, C, H, W)
     pin = lambda: torch.empty(shape, dtype=torch.float32, pin_memory=True)
     h_true, h_x0, h_obs, h_out = pin(), pin(), pin(), pin()
-    n_grid = len(wl.get("grid") or [None])          # item b = (image b // n_grid, grid point b % n_grid)
     for b in range(B):
-        i = (b // n_grid) % n_distinct
-        h_true[b] = torch.from_numpy(np.asarray(trues[i], dtype=np.float32).reshape(C, H, W))
-        h_x0[b] = torch.from_numpy(np.asarray(x0s[i], dtype=np.float32).reshape(C, H, W))
-        h_obs[b] = torch.from_numpy(np.asarray(obss[i], dtype=np.float32).reshape(C, H, W))
+        img, x0, obs = synth[item_image[b]]
+        h_true[b] = torch.from_numpy(np.asarray(img, dtype=np.float32).reshape(C, H, W))
+        h_x0[b] = torch.from_numpy(np.asarray(x0, dtype=np.float32).reshape(C, H, W))
+        h_obs[b] = torch.from_numpy(np.asarray(obs, dtype=np.float32).reshape(C, H, W))
 
     max_iter = a.warmup + 2 * a.steps + 2 * a.e2e_iters + 4
     eng = Engine(B, C, H, W, method=mid, deg_op=wl["deg_op"], max_iter=max_iter, conv_engine=a.engine, device=local_rank,
@@ -326,10 +363,12 @@ def main():
                            q["poisson_alpha"], q["r"])
     grid = wl.get("grid")
     if grid:        # one batch mixes the grid points
-        eng.set_params([params_for({**prm, **grid[b % len(grid)]}) for b in range(B)])
+        eng.set_params([params_for({**prm, **grid[item_grid[b]]}) for b in range(B)])
     else:
         eng.set_params(params_for(prm))
     eng.load_dncnn(weights)
+    if a.tc_variant:
+        eng.set_tc_variant(a.tc_variant)
 
     # ---- device-resident timing: inputs already in HBM when the timed region starts
     eng.set_problem(h_x0.to(dev, non_blocking=True), h_obs.to(dev, non_blocking=True), h_true.to(dev, non_blocking=True))
@@ -371,28 +410,58 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t_ms, op=torch.distributed.ReduceOp.MAX)
     ms_max = float(t_ms.item())
-    px_per_step = B * H * W * world
+    px_per_step = n_items * H * W                       # all ranks together
     value = px_per_step * a.steps / (ms_max * 1e-3) / 1e6
 
-    # ---- end to end through the host-buffer C-ABI call (H2D of x0/obs/x_true + loop + D2H of x and traces)
-    def e2e_call(n_it):
-        t = time.perf_counter()
-        x, s, tr = eng.restore_host(h_x0.numpy(), h_obs.numpy(), h_true.numpy(), n_it, want_s=False, out=h_out.numpy())
-        torch.cuda.synchronize(dev)
-        return time.perf_counter() - t, tr
-    e2e_call(1)
-    if world > 1:
-        torch.distributed.barrier()
-    dt_e2e, tr = e2e_call(a.e2e_iters)
+    # ---- end to end through the product API with HOST buffers.  The timed region holds, per call: H2D of x_0 / x_obsrv / x_true,
+    # the loop, D2H of x and the traces, and — at N > 1 — the path's one collective (NCCL all-gather of the per-item final rows).
+    # Weak workloads: Engine.restore_host (pds_restore_host) + parallel.gather_rows.  cfg5: main.grid_search, which also does the
+    # host-side observation synthesis for the rank's images, batches the items and gathers.
+    e2e_parts = {}
+    if strong:
+        images = [synthetic_image(i, C, H, W) for i in range(n_images)]
+        method_common = dict(method=wl["method"], gamma1=prm["gamma1"], gamma2=prm["gamma2"], alpha_n=prm["alpha_n"], alpha_s=prm["alpha_s"],
+                             myLambda=prm["myLambda"])
+        settings = dict(gaussian_nl=prm["gaussian_nl"], sp_nl=prm["sp_nl"], poisson_noise=wl["poisson"], poisson_alpha=prm["poisson_alpha"],
+                        deg_op=wl["deg_op"], r=prm["r"])
+
+        def e2e_call(n_it):
+            tm = {}
+            t = time.perf_counter()
+            table = pmain.grid_search(images, wl["grid"], settings, dict(method_common, max_iter=n_it), C, hker, weights,
+                                      batch_size=wl["batch"], timings=tm)
+            torch.cuda.synchronize(dev)
+            return time.perf_counter() - t, table, tm
+        eng.close()                                        # the device-resident engine is done; grid_search owns its own (cached) one
+        e2e_call(1)
+        if world > 1:
+            torch.distributed.barrier()
+        dt_e2e, table, e2e_parts = e2e_call(a.e2e_iters)
+        allrows = table.reshape(-1, 3)[:, [0, 2]]          # [items, (PSNR, c)] on every rank
+        e2e_api = "main.grid_search (host images in; observation synthesis, H2D, loop, D2H, NCCL all-gather of [PSNR, SSIM, c] rows inside)"
+        h2d_call, d2h_call = 3 * B * n * 4, B * n * 4 * 2 + a.e2e_iters * B * 5 * 8
+    else:
+        def e2e_call(n_it):
+            t = time.perf_counter()
+            x, s, tr = eng.restore_host(h_x0.numpy(), h_obs.numpy(), h_true.numpy(), n_it, want_s=False, out=h_out.numpy())
+            c_tr, psnr_tr = metrics_from_traces(tr, n)
+            rows = np.stack([psnr_tr[-1], c_tr[-1]], axis=1)
+            t1 = time.perf_counter()
+            allr = gather_rows(rows, B * world) if world > 1 else rows     # the one collective of the path (NCCL all-gather)
+            torch.cuda.synchronize(dev)
+            t2 = time.perf_counter()
+            return t2 - t, allr, dict(collective_s=t2 - t1)
+        e2e_call(1)
+        if world > 1:
+            torch.distributed.barrier()
+        dt_e2e, allrows, e2e_parts = e2e_call(a.e2e_iters)
+        e2e_api = "pds_restore_host (pinned host buffers in, pinned host buffer out) + all-gather of the final [PSNR, c] rows"
+        h2d_call, d2h_call = 3 * B * n * 4, B * n * 4 + a.e2e_iters * B * 5 * 8
     t_e = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t_e, op=torch.distributed.ReduceOp.MAX)
     e2e_value = px_per_step * a.e2e_iters / float(t_e.item()) / 1e6
     nbytes = B * n * 4
-    c_tr, psnr_tr = metrics_from_traces(tr, n)
-    # the one collective of the path: gather per-item final PSNR / c across ranks (NCCL all-gather)
-    rows = np.stack([psnr_tr[-1], c_tr[-1]], axis=1)
-    allrows = gather_rows(rows, B * world) if world > 1 else rows
 
     if rank == 0:
         pk = peaks()
@@ -404,7 +473,7 @@ def main():
         if a.engine != "tcgen05":
             mid_kernel = "conv_mid_simt_kernel"
         elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0) > 0:
-            hbm = bool(int(os.environ.get("PDS_TC_VARIANT", "0")) & 256)
+            hbm = bool(a.tc_variant & 256)
             mid_kernel = ("roll::conv_roll_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand read from HBM)" if hbm else
                           "roll::conv_roll_d_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand rebuilt on chip from the fp16 row)")
             if not hbm:                      # e4m3(a) neither stored nor read, except the store of the layer feeding the last one
@@ -429,20 +498,25 @@ def main():
         prim_bytes = (12 + mask_b) * n * B
         line = dict(
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup, ms_per_step=ms_max / a.steps,
-            higher_is_better=True, scaling="weak", vs_baseline=None,
+            higher_is_better=True, scaling="strong" if strong else "weak", vs_baseline=None,
             dtype="f32 state; DnCNN body: fp16 product + e4m3 first-order operand corrections, fp32 accumulation" if a.engine == "tcgen05" else "f32",
             data="synthetic",
             config=dict(workload=a.workload, method=wl["method"], deg_op=wl["deg_op"], arch=wl["arch"], batch_per_gpu=B,
-                        shape=[C, H, W], conv_engine=a.engine, denoiser_chunk_images=int(chunk),
+                        items_total=n_items, grid_points=n_grid, shape=[C, H, W], conv_engine=a.engine, denoiser_chunk_images=int(chunk),
                         l2="inputs larger than L2 (state arrays %.0f MiB each, activations %.0f MiB per pass)" % (nbytes / 2**20, chunk * H * W * 256 / 2**20),
-                        parallelism=f"independent images sharded over {world} rank(s), no data-path collective"),
+                        parallelism=(f"{n_items} items (images x grid points), fixed total, contiguous blocks over {world} rank(s); one NCCL all-gather of the final rows"
+                                     if strong else f"independent images sharded over {world} rank(s), no data-path collective; one NCCL all-gather of the final rows")),
             gpu_launches=int(launches),
             clocks=sampler.result(),
-            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=3 * nbytes, d2h_bytes_per_step=nbytes + a.e2e_iters * B * 4 * 8,
-                     iterations_per_call=a.e2e_iters, api="pds_restore_host (pinned host buffers in, pinned host buffer out)"),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d_call / a.e2e_iters, d2h_bytes_per_step=d2h_call / a.e2e_iters,
+                     h2d_bytes_per_call=h2d_call, d2h_bytes_per_call=d2h_call, iterations_per_call=a.e2e_iters, seconds_per_call=float(t_e.item()),
+                     bytes_note="per rank; one call = one restoration job of iterations_per_call steps, so per-step bytes = per-call bytes / iterations_per_call",
+                     parts_rank0={k: float(v) for k, v in e2e_parts.items()}, api=e2e_api),
             roofline=dict(bound="tensor", kernel=mid_kernel,
                           achieved=achieved, peak=pk["tensor"], unit="TFLOP/s", frac=(achieved / pk["tensor"]) if achieved else None,
-                          traffic=traffic, algorithmic_bytes_per_launch=mid_bytes_px * chunk * H * W,
+                          traffic=traffic, traffic_source=("ncu --set full capture of this kernel at this launch shape, committed under profiles/ "
+                                                           "(ncu_traffic.json names the capture); not re-measured in this run") if traffic else None,
+                          algorithmic_bytes_per_launch=mid_bytes_px * chunk * H * W,
                           issued_tflops_fp16_equiv=(2.0 * achieved) if (achieved and a.engine == "tcgen05") else None,
                           peak_source=pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                           launches=int(mid_n), avg_ms=mid_ms / max(1, mid_n),
@@ -470,9 +544,12 @@ def main():
                          iterations=a.e2e_iters),
         )
         if world == 1 and not a.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            line["cpu_baseline"], cpu_state = cpu_baseline(wl)
+            line["parity"] = parity_against_cpu_leg(wl, cpu_state, weights, hker)
         print(json.dumps(line))
     eng.close()
+    from pnp_pds_b200.iteration import clear_engine_cache
+    clear_engine_cache()
     if world > 1:
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()

@@ -12,8 +12,10 @@
  *     leading batch of independent restorations; gray images have C = 1.
  *   - `*_dev` pointers are CUDA device pointers on the handle's device, `*_host` are host pointers.
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
- *   - a handle owns its workspace (allocated in pds_create / pds_load_dncnn, nothing afterwards);
- *     it is not thread-safe: one handle per stream.
+ *   - a handle owns its workspace: device memory, the side stream and the events are created in pds_create and
+ *     pds_load_dncnn and nowhere else (the only later allocations are the CUDA events of the optional profiler,
+ *     pds_profile_enable); it is not thread-safe: one handle per stream.
+ *   - kernel selection never depends on the environment.
  *   - there is no CPU fallback: if no CUDA device is usable every call fails with an error.
  */
 #ifndef PNP_PDS_H_
@@ -50,12 +52,6 @@ enum {
   PDS_METHOD_TV_FBS = 10  /* A-FBS-TV : iteration.py:95-99 */
 };
 
-/* engine used for the 64->64 channel layers of the denoiser */
-enum {
-  PDS_CONV_TCGEN05 = 0, /* TMA-fed tcgen05 implicit GEMM: fp16 product + e4m3 operand corrections, fp32 TMEM accumulators */
-  PDS_CONV_SIMT = 1     /* fp32 CUDA-core direct convolution (cross-check engine) */
-};
-
 typedef struct {
   int32_t batch;        /* B: independent restorations (images x grid points) */
   int32_t channels;     /* C: 1 or 3 (reference ch) */
@@ -64,7 +60,7 @@ typedef struct {
   int32_t method;       /* PDS_METHOD_* */
   int32_t deg_op;       /* PDS_OP_* */
   int32_t max_iter;     /* capacity of the per-iteration traces */
-  int32_t conv_engine;  /* PDS_CONV_* */
+  int32_t reserved;     /* must be 0 */
   int32_t device;       /* CUDA device ordinal */
   int32_t denoiser_chunk; /* images per denoiser pass (0 = library default) */
 } pds_config_t;
@@ -101,7 +97,8 @@ int pds_device_count(void);
 int pds_create(const pds_config_t* cfg, pds_handle_t* out);
 int pds_destroy(pds_handle_t h);
 
-/* blur kernel h (l x l, row-major float64 as stored in blur_models/*.mat; operators.py:77-78) */
+/* blur kernel h (l x l, odd l <= 63, row-major float64 as stored in blur_models/*.mat; operators.py:77-78); handles created
+ * with deg_op = PDS_OP_BLUR only; may be called again to replace the kernel */
 int pds_set_blur_kernel(pds_handle_t h, const double* kernel_host, int l);
 /* keep-mask (H*W bytes, 1 = observed) of get_random_sampling_operator (operators.py:40-58);
  * generated on the host with numpy's legacy MT19937 so it is bit-exact */
@@ -164,6 +161,11 @@ long long pds_kernel_launches(pds_handle_t h);
 size_t pds_workspace_bytes(pds_handle_t h);
 
 /* ---- test hooks (hardware probes used by tests/test_gpu_tcgen05.py; not part of the drop-in surface) ---- */
+/* The denoiser always runs on the tcgen05 engine (TMA-fed implicit GEMM: fp16 product + e4m3 operand corrections, fp32 TMEM
+ * accumulators).  A fp32 CUDA-core direct convolution is kept as an on-device cross-check for the tests; it is selected per
+ * handle with this hook (before pds_load_dncnn), never through the configuration. */
+enum { PDS_CONV_TCGEN05 = 0, PDS_CONV_SIMT = 1 };
+int pds_debug_set_conv_engine(pds_handle_t h, int engine);
 /* kernel-selection switches of the tcgen05 engine: bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel for the body layers,
  * bit 6 forces the row-streaming body kernels (dncnn_roll.cu) wherever the image is at least 128 pixels wide, bit 7 disables
  * them, bit 8 makes them read the e4m3(a) operand from HBM instead of rebuilding it on chip (every layer then stores it) */

@@ -21,7 +21,7 @@ PROF_CATS = ("primal", "dual", "l1ball", "conv_first", "conv_mid", "conv_last")
 
 class PdsConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("batch", "channels", "height", "width", "method", "deg_op", "max_iter",
-                                         "conv_engine", "device", "denoiser_chunk")]
+                                         "reserved", "device", "denoiser_chunk")]
 
 
 class PdsItemParams(C.Structure):
@@ -63,6 +63,7 @@ def _declare(lib):
         "pds_kernel_launches": (C.c_longlong, [vp]),
         "pds_workspace_bytes": (sz, [vp]),
         "pds_debug_set_tc_variant": (i, [vp, i]),
+        "pds_debug_set_conv_engine": (i, [vp, i]),
         "pds_debug_roll_band_rows": (i, [i, i, i, i]),
         "pds_debug_umma_probe": (i, [u, u, u, u, vp]),
         "pds_debug_tma_probe": (i, [vp, i, i, i, i, i, i, vp]),

@@ -29,6 +29,23 @@ void set_error(const std::string& msg);
     }                                                                                      \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: a process-wide "done" flag would leave the kernel without
+// its opt-in on a second GPU.  One bit per device ordinal, set atomically.
+struct PerDeviceOnce {
+  unsigned long long mask = 0ull;
+  // true exactly once per device (and always for ordinals >= 64, where the attribute is simply set again)
+  bool first_use() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (__atomic_fetch_or(&mask, bit, __ATOMIC_ACQ_REL) & bit) == 0ull;
+  }
+  void retract() {   // the attribute call failed: try again on the next launch
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) __atomic_fetch_and(&mask, ~(1ull << dev), __ATOMIC_ACQ_REL);
+  }
+};
+
 // ---------------------------------------------------------------- device-side layout
 // Per-item hyper-parameters as the kernels read them (same layout as pds_item_params_t).
 struct ItemParams {

@@ -328,11 +328,10 @@ template <int COUT>
 cudaError_t launch_last_t(int nimg, int H, int W, const __half* act_in, const DncnnLayerW& L, const float* net_in, float rs, int clamp,
                           float* out, cudaStream_t st) {
   const size_t smem = (size_t)(kHalo * kHalo * kLPix + COUT * 9 * 64) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(conv_last_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (e != cudaSuccess) { once.retract(); return e; }
   }
   const int tiles = ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * nimg;
   conv_last_kernel<COUT><<<tiles, kLastThreads, smem, st>>>(nimg, H, W, act_in, L.w_last, L.bias, net_in, rs, clamp, out);
@@ -350,11 +349,10 @@ cudaError_t launch_conv_first(int nimg, int C, int H, int W, const float* in, co
 
 cudaError_t launch_conv_mid_simt(int nimg, int H, int W, const __half* act_in, const DncnnLayerW& L, float slope, __half* act_out,
                                  cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(conv_mid_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMidSmem);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (e != cudaSuccess) { once.retract(); return e; }
   }
   const int tiles = ((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * nimg;
   conv_mid_simt_kernel<<<tiles, kMidThreads, kMidSmem, st>>>(nimg, H, W, act_in, L.w_mid, L.bias, slope, act_out);

@@ -52,7 +52,10 @@ struct pds_handle_s {
   unsigned* mm = nullptr;      // [B][2] min/max keys for the SSIM data range
   int ssim_mode = 0;           // 0 off, 1 every iteration, 2 last iteration of each run
   bool ssim_now = false;
+  int conv_engine = PDS_CONV_TCGEN05;   // pds_debug_set_conv_engine: the fp32 CUDA-core engine is a cross-check, not a product backend
   // blur
+  float* blur_w_dev = nullptr;          // capacity kMaxBlurTaps, allocated in pds_create when deg_op == blur
+  short2* blur_off_dev[2] = {nullptr, nullptr};
   BlurTaps taps{};
   std::vector<float> blur_w_host;
   std::vector<short2> blur_off_host[2];
@@ -128,6 +131,8 @@ void tc_put_weight(__half* tile16, __half* tile8, int row, int ci, float v, cons
   r8[(((k_lo >> 4) ^ (row & 7)) << 4) + (k_lo & 15)] = (uint8_t)__nv_cvt_float_to_fp8(lo * sp.s_lo, __NV_SATFINITE, __NV_E4M3);
   r8[(((k_hi >> 4) ^ (row & 7)) << 4) + (k_hi & 15)] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * sp.s_hi, __NV_SATFINITE, __NV_E4M3);
 }
+
+constexpr int kMaxBlurTaps = 63 * 63;
 
 int tc_num_sms_cached() {
   static int n = tc_num_sms();
@@ -215,27 +220,27 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
     const bool two_cta = !(h->tc_variant & 16);
     const bool derive = band > 0 && !(h->tc_variant & 256);
-    if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+    if (h->conv_engine == PDS_CONV_TCGEN05) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, derive ? 0 : 1, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     }
     int src = 0;
     for (int l = 1; l < h->depth - 1; ++l) {
-      if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && band > 0) {
+      if (h->conv_engine == PDS_CONV_TCGEN05 && band > 0) {
         // the last layer reads the full plane 1 through TMA, so the body layer feeding it stores e4m3(a)
         const int write_a8 = (!derive || l == h->depth - 2) ? 1 : 0;
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, derive ? 1 : 0, write_a8, st));
-      } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05 && two_cta) {
+      } else if (h->conv_engine == PDS_CONV_TCGEN05 && two_cta) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
-      } else if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+      } else if (h->conv_engine == PDS_CONV_TCGEN05) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc(h->tc, src, nimg, h->layers[l], h->slope, st));
       } else {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_simt(nimg, d.H, d.W, h->act[src], h->layers[l], h->slope, h->act[src ^ 1], st));
       }
       src ^= 1;
     }
-    if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+    if (h->conv_engine == PDS_CONV_TCGEN05) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last_tc(h->tc, src, nimg, d.C, h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
@@ -573,7 +578,9 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
               "the TV baselines are defined for colour images only (operators.py:122-123)");
   PDS_REQUIRE(cfg->deg_op >= PDS_OP_ID && cfg->deg_op <= PDS_OP_RANDOM_SAMPLING, "unknown deg_op");
   PDS_REQUIRE(cfg->max_iter >= 1, "max_iter must be >= 1");
+  PDS_REQUIRE(cfg->reserved == 0, "pds_config_t.reserved must be 0");
   PDS_REQUIRE((long long)cfg->batch * cfg->channels <= 65535, "batch*channels exceeds the grid limit");
+  PDS_REQUIRE((long long)cfg->channels * cfg->height * cfg->width <= 0x7fffffffLL, "C*H*W exceeds 2^31-1 elements per item");
   PDS_REQUIRE(pds_device_count() > cfg->device && cfg->device >= 0,
               "no usable CUDA device: this library has no CPU fallback");
   PDS_CUDA_OK(cudaSetDevice(cfg->device));
@@ -583,7 +590,6 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   pds_handle_s* h = new (std::nothrow) pds_handle_s();
   PDS_REQUIRE(h, "out of host memory");
   h->cfg = *cfg;
-  if (const char* v = std::getenv("PDS_TC_VARIANT")) h->tc_variant = std::atoi(v);   // kernel-selection switches (run_dncnn)
   h->d = Dims{cfg->batch, cfg->channels, cfg->height, cfg->width, cfg->height * cfg->width,
               cfg->channels * cfg->height * cfg->width};
   const size_t n = total_elems(h);
@@ -607,7 +613,17 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   A(&h->sums, (size_t)cfg->max_iter * cfg->batch * NSUM);
   A(&h->scratch, (size_t)cfg->batch);
   A(&h->mm, (size_t)cfg->batch * 2);
+  if (cfg->deg_op == PDS_OP_BLUR) {        // tap tables of pds_set_blur_kernel (l <= 63): nothing is allocated after create / load
+    A(&h->blur_w_dev, (size_t)kMaxBlurTaps); A(&h->blur_off_dev[0], (size_t)kMaxBlurTaps); A(&h->blur_off_dev[1], (size_t)kMaxBlurTaps);
+  }
   if (rc) { pds_destroy(h); return rc; }
+  // side stream + events of pds_restore_host (x_obsrv / x_true upload overlapped with the first primal step)
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming) != cudaSuccess) {
+    pds_destroy(h);
+    PDS_REQUIRE(false, "could not create the copy stream / events");
+  }
   *out = h;
   return 0;
 }
@@ -628,7 +644,7 @@ int pds_destroy(pds_handle_t h) {
 int pds_set_blur_kernel(pds_handle_t h, const double* k, int l) {
   PDS_TRY(check_handle(h));
   PDS_REQUIRE(k && l >= 1 && l <= 63 && (l % 2 == 1), "blur kernel must be l x l with odd l <= 63");
-  PDS_REQUIRE(!h->have_blur, "blur kernel already set");
+  PDS_REQUIRE(h->cfg.deg_op == PDS_OP_BLUR, "the handle was not created with deg_op = blur");
   const int c = l / 2;
   std::vector<float> w;
   std::vector<short2> off[2];
@@ -644,12 +660,10 @@ int pds_set_blur_kernel(pds_handle_t h, const double* k, int l) {
       rx = std::max(rx, std::abs(b - c));
     }
   PDS_REQUIRE(!w.empty(), "blur kernel is all zeros");
-  float* dw = nullptr;
-  PDS_TRY(dev_alloc(h, &dw, w.size()));
+  float* dw = h->blur_w_dev;               // capacity kMaxBlurTaps >= l*l (may be called again: the tables are overwritten)
   PDS_CUDA_OK(cudaMemcpy(dw, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
   for (int q = 0; q < 2; ++q) {
-    short2* dof = nullptr;
-    PDS_TRY(dev_alloc(h, &dof, off[q].size()));
+    short2* dof = h->blur_off_dev[q];
     PDS_CUDA_OK(cudaMemcpy(dof, off[q].data(), off[q].size() * sizeof(short2), cudaMemcpyHostToDevice));
     h->taps.w[q] = dw;
     h->taps.off[q] = dof;
@@ -842,7 +856,7 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
   const size_t act_elems = (size_t)chunk * 2 * px * 64;
   PDS_TRY(dev_alloc(h, &h->act[0], act_elems));
   PDS_TRY(dev_alloc(h, &h->act[1], act_elems));
-  if (h->cfg.conv_engine == PDS_CONV_TCGEN05) {
+  if (h->conv_engine == PDS_CONV_TCGEN05) {
     PDS_TRY(tc_plan_create(chunk, h->d.H, h->d.W, h->act[0], h->act[1], &h->tc));
   }
   h->have_net = true;
@@ -983,11 +997,6 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nb = total_elems(h) * sizeof(float);
   h->cur = h->scur = h->iter = 0;
-  if (!h->copy_stream) {
-    PDS_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    PDS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming));
-    PDS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming));
-  }
   // x_0 on the caller's stream (the first primal step needs it); x_obsrv and x_true on a side stream, ordered after whatever
   // the caller's stream was still doing with those buffers, and joined by the first kernel that reads them (wait_inputs)
   PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0], x0, nb, cudaMemcpyHostToDevice, st));
@@ -1048,6 +1057,15 @@ long long pds_kernel_launches(pds_handle_t h) { return h ? h->launches : -1; }
 size_t pds_workspace_bytes(pds_handle_t h) { return h ? h->bytes : 0; }
 
 int pds_debug_roll_band_rows(int nimg, int H, int W, int force) { return pds::roll_band_rows(nimg, H, W, pds::tc_num_sms(), force != 0); }
+
+/* test hook: the fp32 CUDA-core convolution engine (on-device cross-check of the tcgen05 engine); before pds_load_dncnn */
+int pds_debug_set_conv_engine(pds_handle_t h, int engine) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(engine == PDS_CONV_TCGEN05 || engine == PDS_CONV_SIMT, "unknown conv engine");
+  PDS_REQUIRE(!h->have_net, "pds_debug_set_conv_engine must precede pds_load_dncnn");
+  h->conv_engine = engine;
+  return 0;
+}
 
 /* test hook: perf-experiment switches of the tcgen05 engine (see run_dncnn) */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant) {

@@ -302,12 +302,11 @@ cudaError_t launch_rt_ox(const BlurArgs& a0, const Dims& d, cudaStream_t st) {
   a.tiles_x = (d.W + 8 * OX - 1) / (8 * OX);
   const int tiles_y = (d.H + 31) / 32;
   dim3 grid(a.tiles_x * tiles_y, d.B * d.C);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(blur_rt_kernel<MODE, METHOD, RY, RX, OX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)rt_smem_bytes<RY, RX, OX>());
-    if (e != cudaSuccess) return e;
-    attr_set = true;
+    if (e != cudaSuccess) { once.retract(); return e; }
   }
   blur_rt_kernel<MODE, METHOD, RY, RX, OX><<<grid, 256, rt_smem_bytes<RY, RX, OX>(), st>>>(a);
   return cudaGetLastError();

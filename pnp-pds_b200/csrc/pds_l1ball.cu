@@ -11,9 +11,16 @@
 // so the result agrees with the sort-based reference to fp32 round-off of the inputs.
 //
 // One thread-block CLUSTER (8 CTAs x 1024 threads) owns one item: every pass is a strided sweep
-// over the item's elements (L2-resident), a block reduction, and one hardware cluster barrier;
-// the 8 partial (sum, count) pairs are read through distributed shared memory, so there is no
-// global atomics traffic and no host round trip for the data-dependent pass count.
+// over the item's elements, a block reduction, and one hardware cluster barrier; the 8 partial
+// (sum, count) pairs are read through distributed shared memory, so there is no global atomics
+// traffic and no host round trip for the data-dependent pass count.
+//   * items of at most 8 x 1024 x 32 = 262 144 elements (a 512 x 512 gray image: BASELINE cfg2) are read ONCE: every thread
+//     keeps its 32 values of z in registers, the passes are register sweeps + the cluster reduction;
+//   * larger items re-read z every pass.  A single large item stays in the 126 MB L2; a batch does NOT (ncu, 64 items of
+//     1024^2: L2 hit rate ~0, 8 B per element and pass from HBM) - the sweep then runs at HBM speed, which at the 2-4 passes
+//     of the PDS steady state is 0.2 % of the iteration.
+// The pass count is bounded by the element count (the active set shrinks strictly until it stops), so the loop has no
+// artificial cap that could leave tau short of the root.
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
@@ -23,7 +30,7 @@ namespace cg = cooperative_groups;
 namespace pds {
 namespace {
 
-constexpr int kCluster = 8, kThreads = 1024, kMaxPass = 256;
+constexpr int kCluster = 8, kThreads = 1024, kRegs = 32;
 
 struct L1Args {
   Dims d;
@@ -36,6 +43,7 @@ struct L1Args {
   float* tau_out;
 };
 
+template <bool CACHE>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) l1ball_kernel(L1Args a) {
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ double part[2][2];          // [slot][sum, count] of this CTA
@@ -56,20 +64,47 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) l1b
   const int first = rank * kThreads + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  float zr[CACHE ? kRegs : 1];
+  int nk = 0;                 // valid entries of zr
+  if constexpr (CACHE) {
+    nk = first < n ? (n - first + stride - 1) / stride : 0;
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k) {
+      const int i = first + k * stride;
+      float z = 0.f;
+      if (k < nk) {
+        z = __ldg(s + i);
+        if (t) z = fmaf(-gs, __ldg(t + i), z);
+      }
+      zr[k] = z;
+    }
+  }
+
   double tau = -1.0;          // pass 0 selects everything
   double prev_cnt = -1.0;
   bool inside = false;        // ||z||_1 <= eta  ->  identity
-  for (int pass = 0; pass < kMaxPass; ++pass) {
+  for (int pass = 0; pass <= n + 1; ++pass) {     // terminates by itself: the active set shrinks strictly until it stops
     const float tf = (float)tau;
     double sum = 0.0;
     int cnt = 0;
-    for (int i = first; i < n; i += stride) {
-      float z = __ldg(s + i);
-      if (t) z = fmaf(-gs, __ldg(t + i), z);
-      const float az = fabsf(z);
-      if (az > tf) {
-        sum += (double)az;
-        ++cnt;
+    if constexpr (CACHE) {
+#pragma unroll
+      for (int k = 0; k < kRegs; ++k) {
+        const float az = fabsf(zr[k]);
+        if (k < nk && az > tf) {
+          sum += (double)az;
+          ++cnt;
+        }
+      }
+    } else {
+      for (int i = first; i < n; i += stride) {
+        float z = __ldg(s + i);
+        if (t) z = fmaf(-gs, __ldg(t + i), z);
+        const float az = fabsf(z);
+        if (az > tf) {
+          sum += (double)az;
+          ++cnt;
+        }
       }
     }
     double c = (double)cnt;
@@ -113,11 +148,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads) l1b
   const float thr = inside ? 0.f : fmaxf((float)tau, 0.f);
   if (a.tau_out && rank == 0 && threadIdx.x == 0) a.tau_out[b] = thr;
   float* __restrict__ out = a.s_out + base;
-  for (int i = first; i < n; i += stride) {
-    float z = __ldg(s + i);
-    if (t) z = fmaf(-gs, __ldg(t + i), z);
-    const float m = fmaxf(fabsf(z) - thr, 0.f);
-    out[i] = copysignf(m, z);
+  if constexpr (CACHE) {
+#pragma unroll
+    for (int k = 0; k < kRegs; ++k)
+      if (k < nk) out[first + k * stride] = copysignf(fmaxf(fabsf(zr[k]) - thr, 0.f), zr[k]);
+  } else {
+    for (int i = first; i < n; i += stride) {
+      float z = __ldg(s + i);
+      if (t) z = fmaf(-gs, __ldg(t + i), z);
+      const float m = fmaxf(fabsf(z) - thr, 0.f);
+      out[i] = copysignf(m, z);
+    }
   }
 }
 
@@ -127,7 +168,8 @@ cudaError_t launch_l1ball(const Dims& d, const float* s_in, const float* t, cons
                           float eta_override, float* s_out, float* tau_out, cudaStream_t st) {
   L1Args a{d, s_in, t, prm, sums_prev, eta_override, s_out, tau_out};
   dim3 grid(kCluster, d.B);
-  l1ball_kernel<<<grid, kThreads, 0, st>>>(a);
+  if (d.n <= kCluster * kThreads * kRegs) l1ball_kernel<true><<<grid, kThreads, 0, st>>>(a);
+  else l1ball_kernel<false><<<grid, kThreads, 0, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -60,9 +60,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
   asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (-> CUDA error) instead of hanging the GPU.  The bound is wall time (%globaltimer,
+// kWaitTrapNs), not a poll count: under compute-sanitizer, cuda-gdb or time-slicing a healthy kernel can need any number of polls.
+constexpr unsigned long long kWaitTrapNs = 8000000000ull;   // 8 s
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0; !ok; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -71,7 +79,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
-    if (!ok && spin > (1u << 26)) __trap();
+    if (!ok && (spin & 1023u) == 1023u) {
+      const unsigned long long now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > kWaitTrapNs) __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {

@@ -76,10 +76,13 @@ class Engine:
         self.n = self.C * self.H * self.W
         self.method, self.deg_op, self.max_iter = method, deg_op, int(max_iter)
         cfg = PdsConfig(self.B, self.C, self.H, self.W, METHODS[method], DEG_OPS[deg_op], self.max_iter,
-                        CONV_ENGINES[conv_engine], self.device.index, int(denoiser_chunk))
+                        0, self.device.index, int(denoiser_chunk))
         h = C.c_void_p()
         _lib.check(self.lib.pds_create(C.byref(cfg), C.byref(h)))
         self._h = h
+        self.conv_engine = conv_engine
+        if CONV_ENGINES[conv_engine] != 0:      # the fp32 CUDA-core cross-check engine: a test hook, not a configuration field
+            _lib.check(self.lib.pds_debug_set_conv_engine(self._h, CONV_ENGINES[conv_engine]))
         self.shape = (self.B, self.C, self.H, self.W)
 
     # ------------------------------------------------------------------ lifetime
@@ -215,7 +218,8 @@ class Engine:
         return x, s, y
 
     def traces(self) -> np.ndarray:
-        """float64 array [iterations_done, B, 4] of (||t||^2, ||dx||^2, ||x||^2, ||x+ - x_true||^2)."""
+        """float64 array [iterations_done, B, TRACE_WIDTH = 5] of (||t||^2, ||dx||^2, ||x||^2, ||x+ - x_true||^2, SSIM map sum);
+        see PDS_TRACE_WIDTH in include/pnp_pds.h."""
         it = self.iterations_done
         out = np.zeros((it, self.B, TRACE_WIDTH), dtype=np.float64)
         if it:

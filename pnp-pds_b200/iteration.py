@@ -45,6 +45,76 @@ def item_params(method_id: str, n: int, gamma1, gamma2, alpha_s, alpha_n, myLamb
                 eta=l1_ball_radius(n, alpha_s, sp_nl, r_l1), lam=myLambda, alpha=poisson_alpha)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Engine cache.  The reference rebuilds its denoiser (and re-reads the .pth) on every test_iter call (iteration.py:34-41,
+# operators.py:81-83); creating an Engine costs a cudaMalloc of the whole workspace plus the weight swizzle and upload, so
+# consecutive run_batch / test_iter / grid_search calls of one shape, method, operator and checkpoint share one handle.
+# pds_restore_host resets the whole loop state, so a reused handle starts from a clean slate.
+# ---------------------------------------------------------------------------------------------------------------------
+_ENGINE_CACHE: "dict[tuple, Engine]" = {}
+_ENGINE_CACHE_MAX = 4
+_ENGINE_CACHE_BYTES = 48 << 30          # keep at most this much device workspace alive in cached engines
+
+
+def clear_engine_cache():
+    while _ENGINE_CACHE:
+        _ENGINE_CACHE.popitem()[1].close()
+
+
+def _weights_key(weights):
+    if weights is None:
+        return None
+    k = getattr(weights, "_cache_key", None)
+    if k is None:
+        import hashlib
+        k = hashlib.blake2b(weights.to_blob(), digest_size=16).hexdigest()
+        try:
+            weights._cache_key = k
+        except Exception:
+            pass
+    return k
+
+
+def _operator_key(kind, phi):
+    if kind == "blur":
+        import hashlib
+        return hashlib.blake2b(np.ascontiguousarray(phi.h, dtype=np.float64).tobytes(), digest_size=16).hexdigest()
+    if kind == "random_sampling":
+        return float(phi.r)
+    return None
+
+
+def _acquire_engine(B, C, H, W, mid, kind, phi, max_iter, conv_engine, device, denoiser_chunk, weights):
+    import torch
+    dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else device
+    key = (B, C, H, W, mid, kind, _operator_key(kind, phi), conv_engine, dev, int(denoiser_chunk), _weights_key(weights))
+    eng = _ENGINE_CACHE.pop(key, None)
+    if eng is not None and eng.max_iter < max_iter:        # trace capacity too small: rebuild
+        eng.close()
+        eng = None
+    if eng is None:
+        eng = Engine(B, C, H, W, method=mid, deg_op=kind, max_iter=max(1, int(max_iter)), conv_engine=conv_engine, device=device,
+                     denoiser_chunk=denoiser_chunk)
+        try:
+            if kind == "blur":
+                eng.set_blur_kernel(phi.h)
+            elif kind == "random_sampling":
+                eng.set_mask(sampling_mask(H, W, phi.r))
+            if weights is not None:
+                eng.load_dncnn(weights)
+        except Exception:
+            eng.close()
+            raise
+    return key, eng
+
+
+def _release_engine(key, eng):
+    _ENGINE_CACHE[key] = eng                               # most recently used last
+    while len(_ENGINE_CACHE) > _ENGINE_CACHE_MAX or (len(_ENGINE_CACHE) > 1 and
+                                                     sum(e.workspace_bytes for e in _ENGINE_CACHE.values()) > _ENGINE_CACHE_BYTES):
+        _ENGINE_CACHE.pop(next(iter(_ENGINE_CACHE))).close()
+
+
 def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict, path_prox, max_iter: int,
               method: str = "A-Proposed", ch: int = 3, conv_engine: str = "tcgen05", device=None, ssim: str = "final",
               denoiser_chunk: int = 0, m1: int = 15, m2: int = 15, gammaInADMMStep1: float = 0.1):
@@ -83,27 +153,23 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
     items = [item_params(mid, n, p["gamma1"], p["gamma2"], p.get("alpha_s", 1), p.get("alpha_n", 1), p.get("myLambda", 1),
                          p.get("gaussian_nl", 0), p.get("sp_nl", 0), p.get("poisson_alpha", 300), p.get("r", phi.r if kind == "random_sampling" else 1))
              for p in plist]
-    eng = Engine(B, C, H, W, method=mid, deg_op=kind, max_iter=max(1, int(max_iter)), conv_engine=conv_engine, device=device,
-                 denoiser_chunk=denoiser_chunk)
+    key, eng = _acquire_engine(B, C, H, W, mid, kind, phi, max(1, int(max_iter)), conv_engine, device, denoiser_chunk, weights)
     try:
-        if kind == "blur":
-            eng.set_blur_kernel(phi.h)
-        elif kind == "random_sampling":
-            eng.set_mask(sampling_mask(H, W, phi.r))
         eng.set_params(items)
         if mid in ("ADMM_B2", "ADMM_C", "RED_C"):
             eng.set_admm(m1, m2, gammaInADMMStep1)
-        if weights is not None:
-            eng.load_dncnn(weights)
         eng.set_ssim(ssim if x_true is not None else "none")
         import torch
+        launches0 = eng.kernel_launches
         t0 = time.perf_counter()
         x, s, tr = eng.restore_host(x_0, x_obsrv, x_true, int(max_iter), want_s=True)
         torch.cuda.synchronize(eng.device)
         wall = time.perf_counter() - t0
-        launches = eng.kernel_launches
-    finally:
+        launches = eng.kernel_launches - launches0
+    except Exception:
         eng.close()
+        raise
+    _release_engine(key, eng)
     c, psnr = metrics_from_traces(tr, n)                              # [it, B]
     x = x.reshape(x_0.shape)
     s = s.reshape(x_0.shape)
@@ -117,16 +183,16 @@ def test_iter(x_0, x_obsrv, x_true, phi, adj_phi, gamma1, gamma2, alpha_s, alpha
     """Same arguments (and argument order: ..., gamma2, alpha_s, alpha_n, ...) and result tuple as the
     reference (iteration.py:10,196): (x_n, s_n + 0.5, c, psnr_data, ssim_data, average_time).
 
-    Differences, by design: x_n is float32 (as the reference's denoiser output is); ssim_data holds
-    the final SSIM in its last entry and NaN before it (run_batch(ssim="all") evaluates it on the device
-    every iteration like the reference, at a few percent of the iteration time); average_time is wall seconds
+    Differences, by design: x_n is float32 (as the reference's denoiser output is); ssim_data is evaluated on the
+    device every iteration like the reference (iteration.py:189; run_batch(ssim="final") keeps only the last
+    entry and leaves NaN before it); average_time is wall seconds
     per iteration including the H2D/D2H copies, not process CPU seconds; an unknown method raises
     ValueError instead of printing and crashing on an unbound variable (iteration.py:183-185)."""
     p = dict(gamma1=gamma1, gamma2=gamma2, alpha_s=alpha_s, alpha_n=alpha_n, myLambda=myLambda, gaussian_nl=gaussian_nl,
              sp_nl=sp_nl, poisson_alpha=poisson_alpha, r=r)
     x_0 = np.asarray(x_0)
     res = run_batch(x_0[None], np.asarray(x_obsrv)[None], None if x_true is None else np.asarray(x_true)[None], phi, adj_phi,
-                    p, path_prox, max_iter, method, ch, m1=m1, m2=m2, gammaInADMMStep1=gammaInADMMStep1)
+                    p, path_prox, max_iter, method, ch, m1=m1, m2=m2, gammaInADMMStep1=gammaInADMMStep1, ssim="all")
     return (res["x"][0], res["s"][0].astype(np.float64) + 0.5, res["c"][:, 0], res["psnr"][:, 0], res["ssim"][:, 0],
             res["time_per_iter"])
 

@@ -145,7 +145,7 @@ def eval_restoration(gaussian_nl=0.01, sp_nl=0.0, poisson_noise=False, poisson_a
 
 
 def grid_search(images, grid, experimental_settings, method_common, ch, path_kernel, path_prox, batch_size=64,
-                conv_engine="tcgen05"):
+                conv_engine="tcgen05", timings=None):
     """Hyper-parameter sweep of main.main() (main.py:125-159) over `images` x `grid`, sharded over the ranks
     of a torchrun job.  grid: list of dicts overriding gamma1/gamma2/alpha_n/alpha_s/myLambda.
     Work item = (image i, grid point g); items are split in contiguous blocks over ranks, each rank batches
@@ -166,18 +166,26 @@ def grid_search(images, grid, experimental_settings, method_common, ch, path_ker
         for it in ids:
             i, g = divmod(it, n_grid)
             if i not in obs_cache:
+                t0 = time.perf_counter()
                 obs_cache[i] = synthesize_observation(np.asarray(images[i]), phi, deg_op, gaussian_nl, sp_nl, poisson_noise,
                                                       poisson_alpha)
+                t_syn += time.perf_counter() - t0
             x0s.append(obs_cache[i][0]); obss.append(obs_cache[i][1]); trues.append(np.asarray(images[i]))
             base = dict(zip(("method", "architecture", "max_iter", "gamma1", "gamma2", "alpha_n", "alpha_s", "myLambda", "m1", "m2",
                              "gammaInADMMStep1"), parse_args_method({**method_common, **grid[g]})))
             prms.append(dict(gamma1=base["gamma1"], gamma2=base["gamma2"], alpha_s=base["alpha_s"], alpha_n=base["alpha_n"],
                              myLambda=base["myLambda"], gaussian_nl=gaussian_nl, sp_nl=sp_nl, poisson_alpha=poisson_alpha, r=r))
+        t0 = time.perf_counter()
         res = iteration.run_batch(np.stack(x0s), np.stack(obss), np.stack(trues), phi, adj_phi, prms, path_prox, max_iter, method,
                                   ch, conv_engine=conv_engine, device=local_rank if world > 1 else None)
+        t_run += time.perf_counter() - t0
         for k, it in enumerate(ids):
             rows[it - lo] = (res["psnr"][-1, k], res["ssim"][-1, k], res["c"][-1, k])
-    return gather_rows(rows, n_items).reshape(n_img, n_grid, 3)
+    t0 = time.perf_counter()
+    table = gather_rows(rows, n_items).reshape(n_img, n_grid, 3)
+    if timings is not None:
+        timings.update(synthesis_s=t_syn, restore_s=t_run, collective_s=time.perf_counter() - t0, items_on_rank=hi - lo)
+    return table
 
 
 def sweep_experiments():

@@ -13,6 +13,7 @@ blob: a 48-byte header followed by fp32 ``weight[Cout][Cin][3][3]`` and
 from __future__ import annotations
 
 import collections
+import io
 import os
 import pickle
 import struct
@@ -105,7 +106,15 @@ def _restricted_pickle_module():
             except KeyError:
                 raise pickle.UnpicklingError(f"checkpoint references a global outside the allow-list: {module}.{name}")
 
-    return types.SimpleNamespace(Unpickler=RestrictedUnpickler, load=pickle.load, loads=pickle.loads,
+    # torch's legacy (non-zip) loader also calls pickle_module.load(f) for the magic number, protocol version, sys-info and the
+    # storage keys, and the tar branch calls it too: every entry point goes through the allow-listed unpickler.
+    def _load(f, **kw):
+        return RestrictedUnpickler(f, **kw).load()
+
+    def _loads(b, **kw):
+        return RestrictedUnpickler(io.BytesIO(b), **kw).load()
+
+    return types.SimpleNamespace(Unpickler=RestrictedUnpickler, load=_load, loads=_loads,
                                  __name__="pnp_pds_b200.restricted_pickle")
 
 
@@ -132,14 +141,26 @@ def load_pth(path: str) -> DnCNNWeights:
     return DnCNNWeights(layers, slope=slopes.pop(), residual_sign=1.0, clamp=True)
 
 
+_LOADED: dict = {}      # (realpath, mtime_ns, size) -> DnCNNWeights: a checkpoint is parsed once per process, not once per call
+
+
 def load_weights(path: str) -> DnCNNWeights:
     """Load ``path`` (.pth or .pdsw).  If ``path`` does not exist but a sibling
     ``<stem>.pdsw`` does, that is used (the GPU box only carries converted blobs)."""
-    if path.endswith(".pdsw"):
-        with open(path, "rb") as f:
-            return DnCNNWeights.from_blob(f.read())
     if os.path.exists(path):
-        return load_pth(path)
+        st = os.stat(path)
+        key = (os.path.realpath(path), st.st_mtime_ns, st.st_size)
+        w = _LOADED.get(key)
+        if w is None:
+            if path.endswith(".pdsw"):
+                with open(path, "rb") as f:
+                    w = DnCNNWeights.from_blob(f.read())
+            else:
+                w = load_pth(path)
+            if len(_LOADED) >= 8:
+                _LOADED.pop(next(iter(_LOADED)))
+            _LOADED[key] = w
+        return w
     alt = os.path.splitext(path)[0] + ".pdsw"
     if os.path.exists(alt):
         return load_weights(alt)

@@ -52,6 +52,17 @@ def sampling_mask(H: int, W: int, r: float) -> np.ndarray:
 _engines: dict = {}
 
 
+_MAX_CACHED_ENGINES = 16
+
+
+def _cache_put(key, engine):
+    """Bounded cache (oldest first out, closed on eviction) shared by the operator engines and the flat prox engines: every
+    Engine owns device memory proportional to its image size."""
+    while len(_engines) >= _MAX_CACHED_ENGINES:
+        _engines.pop(next(iter(_engines))).close()
+    _engines[key] = engine
+
+
 def _engine_for(kind: str, C: int, H: int, W: int, h, r):
     key = (kind, C, H, W, None if h is None else h.tobytes(), r if kind == "random_sampling" else None)
     e = _engines.get(key)
@@ -61,9 +72,7 @@ def _engine_for(kind: str, C: int, H: int, W: int, h, r):
             e.set_blur_kernel(h)
         elif kind == "random_sampling":
             e.set_mask(sampling_mask(H, W, r))
-        if len(_engines) > 16:
-            _engines.pop(next(iter(_engines))).close()
-        _engines[key] = e
+        _cache_put(key, e)
     return e
 
 
@@ -116,7 +125,7 @@ def _flat_engine(n: int):
     e = _engines.get(key)
     if e is None:
         e = Engine(1, 1, 1, n, method="A", deg_op="Id", max_iter=1)
-        _engines[key] = e
+        _cache_put(key, e)
     return e
 
 

@@ -207,6 +207,62 @@ TV_CASES = [
 ]
 
 
+# Reference-recorded runs at the BASELINE.json shapes and the step sizes of ideas/param_memo.py (:7 cfg1, :44/:50 cfg2,
+# :84 cfg3, :62 comparisonB-2).  Stored compactly (gen_base): the final iterate as the float32 the reference returns, the
+# observation as float32 (the product ingests fp32; Poisson counts are small integers), x_true regenerated from its seed.
+BASE_CASES = [
+    dict(tag="BASE_cfg1_A_blur_256", method="A-Proposed", deg_op="blur", ch=1, hw=(256, 256), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=1200),
+    dict(tag="BASE_cfg3_C_blur_256", method="C-Proposed", deg_op="blur", ch=1, hw=(256, 256), gaussian_nl=0.0, sp_nl=0.0,
+         poisson_noise=True, poisson_alpha=100, gamma1=0.0006, gamma2=1 / 0.0006, myLambda=1.0,
+         alpha_n=0.9, alpha_s=0.95, r=1.0, iters=1200),
+    dict(tag="BASE_cfg4_A_blur_c1024", method="A-Proposed", deg_op="blur", ch=3, hw=(1024, 1024), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=100),
+    dict(tag="BASE_cfg2_B_rs_512", method="B-Proposed", deg_op="random_sampling", ch=1, hw=(512, 512), gaussian_nl=0.01, sp_nl=0.1,
+         gamma1=1.0, gamma2=0.49, alpha_n=0.9, alpha_s=0.9, r=0.8, iters=3000),
+    dict(tag="BASE_B2_blur_128", method="comparisonB-2", deg_op="blur", ch=1, hw=(128, 128), gaussian_nl=0.01, sp_nl=0.0,
+         gamma1=1.0, gamma2=0.49, alpha_n=0.95, alpha_s=0.95, r=1.0, m1=35, m2=5, iters=30),
+]
+
+# the "unstable" KAIR DnCNN loops (iteration.py:106-112 colour / 173-180 gray Poisson)
+UNSTABLE_CASES = [
+    dict(tag="UNS_A_blur_c", method="A-PnPPDS-unstable-DnCNN", arch="dncnn_color_blind", deg_op="blur", ch=3, hw=(40, 48),
+         gaussian_nl=0.01, sp_nl=0.0, gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=1.0, iters=30),
+    dict(tag="UNS_A_rs_g", method="A-PnPPDS-unstable-DnCNN", arch="dncnn_15", deg_op="random_sampling", ch=1, hw=(48, 48),
+         gaussian_nl=0.01, sp_nl=0.0, gamma1=0.99, gamma2=0.99, alpha_n=0.95, alpha_s=0.95, r=0.8, iters=30),
+    dict(tag="UNS_C_blur_g", method="C-PnP-unstable-DnCNN", arch="dncnn_15", deg_op="blur", ch=1, hw=(48, 40),
+         gaussian_nl=0.0, sp_nl=0.0, poisson_noise=True, poisson_alpha=100, gamma1=0.0006, gamma2=1 / 0.0006, myLambda=1.0,
+         alpha_n=0.9, alpha_s=0.95, r=1.0, iters=30),
+]
+
+
+def case_seed(tag):
+    return sum(map(ord, tag)) % 997
+
+
+def gen_base(ref, cases, only_tags=()):
+    """One .npz per case (tests/golden/base_<tag>.npz) so a long run can be added without redoing the others."""
+    import json
+    for case in cases:
+        if only_tags and case["tag"] not in only_tags:
+            continue
+        t = time.time()
+        res = run_case(ref, case, snapshots=())
+        n = case["iters"]
+        x = np.asarray(res[f"x_{n}"])
+        assert x.dtype == np.float32, x.dtype                        # the reference's denoiser output (denoiser.py:44)
+        obs = np.asarray(res["obs"])
+        obs32 = obs.astype(np.float32)
+        out = {"x": x, "obs": obs32, "obs_f32_max_abs_err": np.max(np.abs(obs32.astype(np.float64) - obs)),
+               "c": res["c"], "psnr": res["psnr"], "seed": case_seed(case["tag"]),
+               "x_true_sum": float(np.sum(res["x_true"], dtype=np.float64)), "case": np.array(json.dumps(case)),
+               "seconds": time.time() - t}
+        s05 = np.asarray(res[f"s05_{n}"])
+        if np.any(s05 != 0.5):
+            out["s05"] = s05.astype(np.float32)
+        save(f"base_{case['tag']}.npz", **out)
+
+
 def gen_textfile():
     """SUMMARY text-file strings from the reference's own writer (utils/utils_textfile.py) for a fixed `datas` dict."""
     import importlib.util
@@ -233,7 +289,7 @@ def run_case(ref, case, snapshots):
     ch = case["ch"]
     H, W = case["hw"]
     deg_op, r = case["deg_op"], case.get("r", 1.0)
-    img_true = synthetic_image(hash(case["tag"]) % 1000 if False else sum(map(ord, case["tag"])) % 997, ch, H, W)
+    img_true = synthetic_image(sum(map(ord, case["tag"])) % 997, ch, H, W)
     phi, adj = op.get_observation_operators(deg_op, KERNEL, r)
     ident, _ = op.get_observation_operators("Id", KERNEL, r)
     nop = phi if deg_op == "random_sampling" else ident
@@ -245,7 +301,7 @@ def run_case(ref, case, snapshots):
     x0 = np.copy(obs)
     if case.get("poisson_noise", False):
         x0 = x0 / case.get("poisson_alpha", 300)
-    arch = "DnCNN_nobn_nch_1_nlev_0.01" if ch == 1 else "DnCNN_nobn_nch_3_nlev_0.01"
+    arch = case.get("arch", "DnCNN_nobn_nch_1_nlev_0.01" if ch == 1 else "DnCNN_nobn_nch_3_nlev_0.01")
     path_prox = os.path.join(NN, arch + ".pth")
     res = {}
     # test_iter has no snapshot hook: run it for each snapshot length (cheap at these sizes)
@@ -281,6 +337,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--long", action="store_true", help="also run the full-iteration-count cases (minutes)")
     ap.add_argument("--only", default="")
+    ap.add_argument("--tags", default="", help="with --only base: comma-separated case tags (default: all)")
     a = ap.parse_args()
     ref = ref_harness.load()
     import torch
@@ -302,6 +359,10 @@ def main():
         gen_loops(ref, TV_CASES, "tv.npz", snapshots=(1, 2, 10))
     if a.long or "long" in todo:
         gen_loops(ref, LONG_CASES, "long.npz", snapshots=())
+    if "unstable" in todo:
+        gen_loops(ref, UNSTABLE_CASES, "unstable.npz", snapshots=(1, 2, 10))
+    if "base" in todo:                                               # ~1 h on 8 vCPUs
+        gen_base(ref, BASE_CASES, tuple(t for t in a.tags.split(",") if t))
 
 
 if __name__ == "__main__":

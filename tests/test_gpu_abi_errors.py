@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def _cfg(**kw):
     from pnp_pds_b200._lib import PdsConfig
-    d = dict(batch=1, channels=1, height=32, width=32, method=0, deg_op=0, max_iter=4, conv_engine=0, device=0, denoiser_chunk=0)
+    d = dict(batch=1, channels=1, height=32, width=32, method=0, deg_op=0, max_iter=4, reserved=0, device=0, denoiser_chunk=0)
     d.update(kw)
     return PdsConfig(*[d[n] for n, _ in PdsConfig._fields_])
 
@@ -25,6 +25,8 @@ def _err(lib):
     (dict(batch=0), "bad shape"), (dict(channels=2), "channels"), (dict(method=99), "unknown method"),
     (dict(deg_op=7), "unknown deg_op"), (dict(max_iter=0), "max_iter"), (dict(device=99), "device"),
     (dict(method=8, channels=1), "colour"),                       # TV baselines need three channels
+    (dict(reserved=1), "reserved"),
+    (dict(channels=3, height=40000, width=40000), "2^31"),
 ])
 def test_create_rejects_bad_configs(kw, needle):
     from pnp_pds_b200 import _lib
@@ -60,6 +62,11 @@ def test_call_order_and_argument_checks():
         assert lib.pds_set_blur_kernel(h, k.ctypes.data_as(C.POINTER(C.c_double)), 3) == 0
         assert lib.pds_phi(h, p(x), p(x), None) != 0 and "in place" in _err(lib)
         assert lib.pds_phi(h, p(x), p(out), None) == 0 and torch.allclose(out, x)          # delta kernel = identity
+        k2 = np.zeros((5, 5)); k2[2, 3] = 1.0                                                # replacing the kernel: a one-pixel shift
+        assert lib.pds_set_blur_kernel(h, k2.ctypes.data_as(C.POINTER(C.c_double)), 5) == 0
+        xr = torch.rand((1, 1, 32, 32), device="cuda")
+        assert lib.pds_phi(h, p(xr), p(out), None) == 0 and torch.equal(out, torch.roll(xr, 1, dims=3))
+        assert lib.pds_set_blur_kernel(h, k.ctypes.data_as(C.POINTER(C.c_double)), 3) == 0
         # weights: wrong magic, truncated blob, wrong channel count
         assert lib.pds_load_dncnn(h, b"XXXX" + bytes(60), 64) != 0 and "PDSW" in _err(lib)
         blob = load_weights(weights_path("DnCNN_nobn_nch_1_nlev_0.01")).to_blob()
@@ -83,3 +90,11 @@ def test_call_order_and_argument_checks():
     finally:
         assert lib.pds_destroy(h) == 0
     assert lib.pds_run(None, 1, None) != 0 and "null handle" in _err(lib)
+    h2 = C.c_void_p()
+    assert lib.pds_create(C.byref(_cfg(deg_op=0)), C.byref(h2)) == 0
+    try:
+        k = np.zeros((3, 3)); k[1, 1] = 1.0
+        assert lib.pds_set_blur_kernel(h2, k.ctypes.data_as(C.POINTER(C.c_double)), 3) != 0 and "deg_op" in _err(lib)
+        assert lib.pds_debug_set_conv_engine(h2, 7) != 0 and "unknown conv engine" in _err(lib)
+    finally:
+        assert lib.pds_destroy(h2) == 0

@@ -238,3 +238,81 @@ def test_batched_full_loop_tensor_engine_tracks_fp32_engine(assets):
           f"{max(rel_l2(out['tcgen05']['x'][b], out['simt']['x'][b]) for b in range(B)):.2e}, max dPSNR = {dpsnr:.2e} dB")
     assert dpsnr < DPSNR_GATE
     assert np.all(out["tcgen05"]["c"][-1] < 1e-3)                      # converging
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Reference-recorded runs at the BASELINE.json shapes (tests/golden/base_*.npz, make_golden.py BASE_CASES): the kernels the
+# benchmark runs (row-streaming body kernel at 512^2 / 1024^2, the tile / chain kernels at 256^2) against the unmodified
+# reference over its full iteration counts, with the north-star gates.
+# ---------------------------------------------------------------------------------------------------------------------
+BASE = ["BASE_cfg1_A_blur_256", "BASE_cfg3_C_blur_256", "BASE_cfg4_A_blur_c1024", "BASE_cfg2_B_rs_512", "BASE_B2_blur_128"]
+
+
+def _load_base(tag):
+    import os
+    from conftest import GOLDEN
+    p = os.path.join(GOLDEN, f"base_{tag}.npz")
+    if not os.path.exists(p):
+        pytest.skip(f"{p} not generated")
+    g = np.load(p, allow_pickle=False)
+    case = json.loads(str(g["case"]))
+    H, W = case["hw"]
+    x_true = O.synthetic_image(int(g["seed"]), case["ch"], H, W)
+    assert abs(float(np.sum(x_true, dtype=np.float64)) - float(g["x_true_sum"])) < 1e-9 * x_true.size
+    return g, case, x_true
+
+
+@pytest.mark.parametrize("tag", BASE)
+def test_baseline_shapes_full_runs_against_reference(assets, tag):
+    from pnp_pds_b200 import iteration, operators
+    g, case, x_true = _load_base(tag)
+    obs = g["obs"]
+    x0 = obs / np.float32(case["poisson_alpha"]) if case.get("poisson_noise", False) else obs
+    arch = case.get("arch", "DnCNN_nobn_nch_1_nlev_0.01" if case["ch"] == 1 else "DnCNN_nobn_nch_3_nlev_0.01")
+    phi, adj = operators.get_observation_operators(case["deg_op"], assets["blur_1"], case.get("r", 1.0))
+    prm = dict(gamma1=case["gamma1"], gamma2=case["gamma2"], alpha_s=case["alpha_s"], alpha_n=case["alpha_n"],
+               myLambda=case.get("myLambda", 1.0), gaussian_nl=case["gaussian_nl"], sp_nl=case["sp_nl"],
+               poisson_alpha=case.get("poisson_alpha", 300), r=case.get("r", 1.0))
+    n = case["iters"]
+    res = iteration.run_batch(x0[None], obs[None], x_true[None], phi, adj, prm, weights_path(arch), n, case["method"], case["ch"],
+                              m1=case.get("m1", 15), m2=case.get("m2", 15), gammaInADMMStep1=case.get("gammaInADMMStep1", 0.1), ssim="none")
+    e = rel_l2(res["x"][0], g["x"])
+    dpsnr = abs(res["psnr"][-1, 0] - g["psnr"][-1])
+    trace = np.max(np.abs(res["psnr"][:, 0] - g["psnr"]))
+    print(f"{tag}: {n} iterations, rel_l2={e:.2e}, dPSNR={dpsnr:.2e} dB, max trace dPSNR={trace:.2e}, psnr={res['psnr'][-1, 0]:.4f}, "
+          f"c_last={res['c'][-1, 0]:.2e} (ref {g['c'][-1]:.2e}), {res['time_per_iter'] * 1e3:.3f} ms/it")
+    assert e <= REL_L2_GATE
+    assert dpsnr <= DPSNR_GATE
+    assert trace < 5 * DPSNR_GATE
+    if "s05" in g.files:
+        assert np.max(np.abs(res["s"][0] + 0.5 - g["s05"])) < 1e-4
+
+
+UNSTABLE = ["UNS_A_blur_c", "UNS_A_rs_g", "UNS_C_blur_g"]
+
+
+@pytest.mark.parametrize("tag", UNSTABLE)
+def test_unstable_kair_loops(assets, tag):
+    """A-PnPPDS-unstable-DnCNN (iteration.py:106-112) / C-PnP-unstable-DnCNN (iteration.py:173-180): the PDS loop around the KAIR
+    DnCNN (ReLU, x - model(x), no clamps) against the reference's traces."""
+    from conftest import load_golden
+    from pnp_pds_b200 import iteration, operators
+    g = load_golden("unstable.npz")
+    case = json.loads(str(g[f"{tag}/case"]))
+    phi, adj = operators.get_observation_operators(case["deg_op"], assets["blur_1"], case.get("r", 1.0))
+    prm = dict(gamma1=case["gamma1"], gamma2=case["gamma2"], alpha_s=case["alpha_s"], alpha_n=case["alpha_n"],
+               myLambda=case.get("myLambda", 1.0), gaussian_nl=case["gaussian_nl"], sp_nl=case["sp_nl"],
+               poisson_alpha=case.get("poisson_alpha", 300), r=case.get("r", 1.0))
+    for n in (1, 2, 10, case["iters"]):
+        res = iteration.run_batch(g[f"{tag}/x0"][None], g[f"{tag}/obs"][None], g[f"{tag}/x_true"][None], phi, adj, prm,
+                                  weights_path(case["arch"]), n, case["method"], case["ch"])
+        e = rel_l2(res["x"][0], g[f"{tag}/x_{n}"])
+        print(f"{tag} n={n}: rel_l2(x)={e:.2e}")
+        assert e < REL_L2_GATE, (tag, n)
+    assert np.allclose(res["c"][:, 0], g[f"{tag}/c"], rtol=5e-3, atol=2e-6), tag
+    assert np.max(np.abs(res["psnr"][:, 0] - g[f"{tag}/psnr"])) < DPSNR_GATE, tag
+    # the legacy names reach the same loops
+    alias = {"A-PnPPDS-unstable-DnCNN": "comparisonA-7", "C-PnP-unstable-DnCNN": "comparisonC-4"}[case["method"]]
+    res2 = iteration.run_batch(g[f"{tag}/x0"][None], g[f"{tag}/obs"][None], g[f"{tag}/x_true"][None], phi, adj, prm,
+                               weights_path(case["arch"]), 2, alias, case["ch"])
+    assert rel_l2(res2["x"][0], g[f"{tag}/x_2"]) < REL_L2_GATE

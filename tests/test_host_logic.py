@@ -84,6 +84,26 @@ def test_pth_conversion_matches_committed_blobs_and_blocks_foreign_globals(tmp_p
         load_pth(str(p))
 
 
+def test_legacy_checkpoint_first_pickle_goes_through_the_allow_list(tmp_path):
+    """torch's legacy loader reads the magic number / protocol / sys-info / storage keys with pickle_module.load: a file
+    whose FIRST pickle carries a REDUCE on os.system must be rejected, not executed."""
+    import pickle
+    from pnp_pds_b200.models.weights import load_pth
+    marker = tmp_path / "executed"
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, (f"touch {marker}",))
+    p = tmp_path / "evil_first.pth"
+    with open(p, "wb") as f:
+        pickle.dump(Evil(), f, protocol=2)          # where the magic number belongs
+        pickle.dump(1001, f, protocol=2)
+        pickle.dump({}, f, protocol=2)
+    with pytest.raises(pickle.UnpicklingError):
+        load_pth(str(p))
+    assert not marker.exists()
+
+
 @pytest.mark.parametrize("H,W,r", [(32, 32, 0.8), (64, 64, 0.5), (48, 20, 0.7), (256, 256, 0.8), (512, 512, 0.8), (1024, 1024, 0.8)])
 def test_product_mask_bit_exact(g_ops, H, W, r):
     from pnp_pds_b200.operators import sampling_mask

@@ -55,6 +55,12 @@ def make_denoise(layers, scheme, slope=0.01, sign=1.0, clamp=True):
             S = 18 - e
             t = conv(q8(a), q8(w_lo * 2.0**S)) + conv(q8(a_lo * 2.0**10), q8(w_hi * 2.0**(S - 10)))
             return conv(a_hi, w_hi) + (t * 2.0**-S).float().double()
+        if scheme == "fp8w":       # weights exact (w_hi + e4m3 w_lo), activations rounded to fp16 once: 1.5 MMA times, no a_lo plane
+            import math
+            e = math.frexp(float(w.abs().max()))[1]
+            S = 18 - e
+            t = conv(q8(a), q8(w_lo * 2.0**S))
+            return conv(a_hi, w_hi) + (t * 2.0**-S).float().double()
         if scheme == "fp4lo":      # what a block-scaled fp4 correction operand would give (1.5 MMA times per layer)
             t = conv(q4_block(a, 1), q4_block(w_lo, 1)) + conv(q4_block(a_lo, 1), q4_block(w_hi, 1))
             return conv(a_hi, w_hi) + t.float().double()
