@@ -634,34 +634,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_
 //   accumulator columns per stage: [0,64) a_hi*w_hi (kind::f16), [64,128) e4m3 correction * 2^S (kind::f8f6f4)
 // ---------------------------------------------------------------------------------------------
 namespace two {
-constexpr uint32_t kWHalf = 9 * 64 * 128;             // 73728: per-CTA weight image
-constexpr int kSlots2 = 5;
-constexpr uint32_t kOffA2 = kWHalf, kOffBar2 = kOffA2 + kSlots2 * kPlaneSlot;
-constexpr uint32_t kOffBias2 = kOffBar2 + 192, kSmemBytes2 = kOffBias2 + 256 + 1024;
-constexpr uint32_t kAccCols2 = 128, kTmemCols2 = 512;
-constexpr int kAccStages2 = 4;                        // 4 x 128 columns: the epilogue may lag the tensor pipe by three tiles
-constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16 (or e4m3: same code 0), M=256
-constexpr uint32_t kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
-
-
-template <bool P0>
-__device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
-  constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);
-  constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int dy = tap / 3, dx = tap - dy * 3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
-      const uint32_t bo = (uint32_t)(tap * 8192 + (P0 ? 0 : 4096) + k * 32) >> 4;
-      const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
-      if (P0) umma_f16_2sm(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
-      else umma_f8_2sm(d_tmem + 64u, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
-    }
-  }
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     conv_tc2_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -947,6 +919,7 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   if (!rc) rc = make_act_map(&p->map_row[0], act0, nimg, H, W, 130, 1);      // dncnn_roll.cu: 128-pixel strip + x halo
   if (!rc) rc = make_act_map(&p->map_row[1], act1, nimg, H, W, 130, 1);
   if (!rc) rc = roll_setup();
+  if (!rc) rc = chain_setup();
   if (!rc) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<64>::kSmemBytes);
     if (e == cudaSuccess)
@@ -972,7 +945,12 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   return 0;
 }
 
-void tc_plan_destroy(TcPlan* p) { delete p; }
+void tc_plan_destroy(TcPlan* p) {
+  if (!p) return;
+  if (p->chain_layers) cudaFree(p->chain_layers);
+  if (p->chain_flags) cudaFree(p->chain_flags);
+  delete p;
+}
 
 static void fill_common(TcArgs& a, TcPlan* plan, int nimg) {
   a.H = plan->H;

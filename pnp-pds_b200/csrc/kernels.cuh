@@ -122,6 +122,10 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
 cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
                                 float residual_sign, int clamp, float* out, cudaStream_t st);
+// all body layers in one persistent launch (dncnn_chain.cu); set up by tc_plan_chain after the layers are uploaded
+int tc_plan_chain(TcPlan* plan, const DncnnLayerW* layers, int depth, size_t* bytes_out);
+bool tc_chain_available(const TcPlan* plan, int nimg);
+cudaError_t launch_conv_body_chain(TcPlan* plan, int in_buf, int nimg, float slope, cudaStream_t st);
 int tc_num_sms();
 // row-streaming body layer (dncnn_roll.cu): band height for a launch of nimg images (0 = not applicable, use the tile kernels)
 int roll_setup();

@@ -226,7 +226,15 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     }
     int src = 0;
-    for (int l = 1; l < h->depth - 1; ++l) {
+    // small launches (the tile kernels' territory): all body layers in ONE persistent launch with tile-level dataflow between
+    // layers (dncnn_chain.cu).  tc_variant bit 9 disables it (per-layer tile kernels: the bit-exact cross-check).
+    const bool chain = h->conv_engine == PDS_CONV_TCGEN05 && band == 0 && two_cta && !(h->tc_variant & 512) && h->depth > 2 &&
+                       tc_chain_available(h->tc, nimg);
+    if (chain) {
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_body_chain(h->tc, src, nimg, h->slope, st));
+      src ^= (h->depth - 2) & 1;
+    }
+    for (int l = 1; l < h->depth - 1 && !chain; ++l) {
       if (h->conv_engine == PDS_CONV_TCGEN05 && band > 0) {
         // the last layer reads the full plane 1 through TMA, so the body layer feeding it stores e4m3(a)
         const int write_a8 = (!derive || l == h->depth - 2) ? 1 : 0;
@@ -858,6 +866,9 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
   PDS_TRY(dev_alloc(h, &h->act[1], act_elems));
   if (h->conv_engine == PDS_CONV_TCGEN05) {
     PDS_TRY(tc_plan_create(chunk, h->d.H, h->d.W, h->act[0], h->act[1], &h->tc));
+    size_t chain_bytes = 0;
+    PDS_TRY(tc_plan_chain(h->tc, h->layers.data(), depth, &chain_bytes));
+    h->bytes += chain_bytes;
   }
   h->have_net = true;
   return 0;

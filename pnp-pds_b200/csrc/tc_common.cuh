@@ -5,9 +5,20 @@
 #include <cuda.h>
 #include <cuda_fp8.h>
 
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace pds {
+
+// Per-layer entry of the chain kernel's device table (dncnn_chain.cu).
+struct ChainLayer {
+  const __half* w;          // DncnnLayerW::w_mid_tc2 (per-CTA halves of the weight image)
+  const float* bias;
+  float lo_scale;
+  float pad;
+};
+constexpr int kChainMaxPairs = 16384;   // launches of up to 2 Mpx can run as one chain launch (flags: layers x pairs x 4 B)
 
 // Tensor maps and geometry of the two activation buffers of one engine handle.
 struct TcPlan {
@@ -16,7 +27,17 @@ struct TcPlan {
   __half* act[2];
   int nimg, H, W;
   int num_sms;
+  // chain kernel (all body layers in one launch, dncnn_chain.cu); null when the plan's launches are too large for it
+  ChainLayer* chain_layers = nullptr;
+  uint32_t* chain_flags = nullptr;      // [chain_nlayers][chain_stride] per-unit arrival counters, monotone across launches
+  int chain_nlayers = 0, chain_stride = 0, chain_npairs_last = -1;
+  uint32_t chain_epoch = 0;
+  size_t chain_bytes = 0;
 };
+int chain_setup();
+int tc_plan_set_chain(TcPlan* plan, const std::vector<ChainLayer>& layers);
+bool chain_available(const TcPlan* plan, int nimg);
+cudaError_t launch_conv_chain(TcPlan* plan, int in_buf, int nimg, float slope, cudaStream_t st);
 
 namespace {
 
@@ -284,6 +305,35 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t adesc, uint64
     else PDS_MMA2("f8f6f4", ".collector::a::lastuse");
   }
 #undef PDS_MMA2
+}
+
+// ---- geometry and MMA issue of the CTA-pair tile kernels (conv_tc2_kernel in dncnn_tc.cu, conv_chain_kernel in dncnn_chain.cu)
+constexpr uint32_t kWHalf = 9 * 64 * 128;             // 73728: per-CTA weight image
+constexpr int kSlots2 = 5;
+constexpr uint32_t kOffA2 = kWHalf, kOffBar2 = kOffA2 + kSlots2 * kPlaneSlot;
+constexpr uint32_t kOffBias2 = kOffBar2 + 192, kSmemBytes2 = kOffBias2 + 256 + 1024;
+constexpr uint32_t kAccCols2 = 128, kTmemCols2 = 512;
+constexpr int kAccStages2 = 4;                        // 4 x 128 columns: the epilogue may lag the tensor pipe by three tiles
+constexpr uint32_t kIdescBase2 = (1u << 4) | ((256u >> 4) << 24);     // D=f32, A=B=f16 (or e4m3: same code 0), M=256
+constexpr uint32_t kIdescN64 = kIdescBase2 | ((64u >> 3) << 17);
+
+
+template <bool P0>
+__device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
+  constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);
+  constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
+      const uint32_t bo = (uint32_t)(tap * 8192 + (P0 ? 0 : 4096) + k * 32) >> 4;
+      const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
+      if (P0) umma_f16_2sm(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
+      else umma_f8_2sm(d_tmem + 64u, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
+    }
+  }
 }
 }  // namespace two
 

@@ -150,7 +150,10 @@ def grid_search(images, grid, experimental_settings, method_common, ch, path_ker
     of a torchrun job.  grid: list of dicts overriding gamma1/gamma2/alpha_n/alpha_s/myLambda.
     Work item = (image i, grid point g); items are split in contiguous blocks over ranks, each rank batches
     its items (mixed grid points in one batch: per-item parameter vectors) and the final
-    (psnr, ssim, c_last) rows are all-gathered once.  Returns array [n_images, n_grid, 3] on every rank."""
+    (psnr, ssim, c_last) rows are all-gathered once.  Returns array [n_images, n_grid, 3] on every rank.
+    timings: optional dict that receives this rank's wall seconds per phase (synthesis, restore, gather)."""
+    import time
+    t_syn = t_run = 0.0
     gaussian_nl, sp_nl, poisson_noise, poisson_alpha, deg_op, r = parse_args_exp(experimental_settings)
     method, _, max_iter, *_ = parse_args_method(method_common)
     rank, local_rank, world = dist_info()

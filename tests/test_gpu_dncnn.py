@@ -146,7 +146,7 @@ def test_tile_kernels_one_and_two_cta_agree(shape):
     w = load_weights(weights_path(SIMPLE[1] if C == 3 else SIMPLE[0]))
     x = np.random.default_rng(21).random(shape).astype(np.float32)
     outs = []
-    for variant in (16, 32):                       # force the 1-CTA / the 2-CTA tile kernel for the body layers
+    for variant in (16 | 512, 32 | 512):           # force the 1-CTA / the 2-CTA tile kernel, one launch per body layer
         with Engine(B, C, H, W, conv_engine="tcgen05") as e:
             e.load_dncnn(w)
             e.set_tc_variant(variant)
@@ -154,3 +154,54 @@ def test_tile_kernels_one_and_two_cta_agree(shape):
     assert np.array_equal(outs[0], outs[1])
     ref = O.dncnn_forward(w.layers, x[0], w.slope, w.residual_sign, w.clamp)
     assert float(np.max(np.abs(outs[0][0] - ref))) < TOL
+
+
+@pytest.mark.parametrize("shape,arch", [((1, 1, 256, 256), SIMPLE[0]), ((1, 1, 48, 24), SIMPLE[0]), ((3, 3, 50, 37), SIMPLE[1]),
+                                        ((2, 1, 130, 70), SIMPLE[0]), ((1, 1, 16, 8), SIMPLE[0]), ((5, 1, 96, 200), "dncnn_15"),
+                                        ((1, 3, 200, 120), "dncnn_color_blind"), ((1, 1, 512, 512), SIMPLE[0])])
+def test_chain_kernel_matches_per_layer_tile_kernels(shape, arch):
+    """All body layers in one persistent launch with tile-level dataflow between layers (dncnn_chain.cu) against one
+    conv_tc2_kernel launch per layer: the same MMAs in the same order per output element -> bit-identical, for a single
+    256^2 / 512^2 image, fewer units than clusters (16 x 8: one tile), odd tile counts, ragged edges, several images, the
+    17-layer and the colour KAIR networks; and again on repeated calls (the per-unit flags count up across launches)."""
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    B, C, H, W = shape
+    w = load_weights(weights_path(arch))
+    rng = np.random.default_rng(31)
+    xs = [rng.random(shape).astype(np.float32) for _ in range(3)]
+    with Engine(B, C, H, W, conv_engine="tcgen05") as e:
+        e.load_dncnn(w)
+        e.set_tc_variant(128 | 512)                 # tile kernels, one launch per layer
+        ref = [e.dncnn_forward(e.to_device(x)).cpu().numpy() for x in xs]
+        n0 = e.kernel_launches
+        e.dncnn_forward(e.to_device(xs[0]))
+        per_layer = e.kernel_launches - n0
+        e.set_tc_variant(128)                       # tile kernels' territory -> the chain kernel
+        n0 = e.kernel_launches
+        out = [e.dncnn_forward(e.to_device(x)).cpu().numpy() for x in xs]
+        chained = (e.kernel_launches - n0) // 3
+    assert per_layer == w.depth and chained == 3, (per_layer, chained)      # first + ONE body launch + last
+    for a, b in zip(ref, out):
+        assert np.array_equal(a, b)
+    o = O.dncnn_forward(w.layers, xs[0][0] if C == 3 else xs[0][0, 0], w.slope, w.residual_sign, w.clamp)
+    assert float(np.max(np.abs(out[0][0] - o.reshape(out[0][0].shape)))) < (1e-4 if arch.startswith("dncnn") else TOL)
+
+
+def test_chain_kernel_partial_last_chunk_and_back_to_back_calls():
+    """A batch that does not divide into denoiser chunks: the last chunk has fewer tile pairs than the others, so its launch
+    starts from zeroed flags (launch_conv_chain); 20 back-to-back passes stay bit-identical to the per-layer kernels."""
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    B, C, H, W = 5, 1, 64, 72
+    w = load_weights(weights_path(SIMPLE[0]))
+    x = np.random.default_rng(33).random((B, C, H, W)).astype(np.float32)
+    with Engine(B, C, H, W, conv_engine="tcgen05", denoiser_chunk=2) as e:
+        e.load_dncnn(w)
+        e.set_tc_variant(128 | 512)
+        ref = e.dncnn_forward(e.to_device(x)).cpu().numpy()
+        e.set_tc_variant(128)
+        xd = e.to_device(x)
+        for _ in range(20):
+            out = e.dncnn_forward(xd)
+        assert np.array_equal(out.cpu().numpy(), ref)
