@@ -168,8 +168,14 @@ enum { PDS_CONV_TCGEN05 = 0, PDS_CONV_SIMT = 1 };
 int pds_debug_set_conv_engine(pds_handle_t h, int engine);
 /* kernel-selection switches of the tcgen05 engine: bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel for the body layers,
  * bit 6 forces the row-streaming body kernels (dncnn_roll.cu) wherever the image is at least 128 pixels wide, bit 7 disables
- * them, bit 8 makes them read the e4m3(a) operand from HBM instead of rebuilding it on chip (every layer then stores it) */
+ * them, bit 8 makes them read the e4m3(a) operand from HBM instead of rebuilding it on chip (every layer then stores it),
+ * bit 9 disables the chain kernel (all body layers of a small launch in one persistent launch) in favour of one tile-kernel
+ * launch per layer */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant);
+/* SM-cycle-counter stamps of the chain kernel's pipeline events (dncnn_chain.cu: flags polled, TMA issued, TMEM stage free, first
+ * plane landed, MMAs issued, accumulator ready, stored, published) for the first 64 units of CTA 0 of the first 4 clusters:
+ * out_host == NULL arms the trace for the following launches, otherwise [4][64][8] uint64 are copied back and it is disarmed */
+int pds_debug_chain_trace(pds_handle_t h, unsigned long long* out_host);
 /* rows per CTA pair when the row-streaming body kernels serve a launch of nimg images of H x W on the current device;
  * 0 = the tile kernels run instead (narrower than 128 pixels, or the cost model prefers tiles; force != 0 skips that comparison) */
 int pds_debug_roll_band_rows(int nimg, int H, int W, int force);

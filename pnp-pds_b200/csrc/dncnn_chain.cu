@@ -9,8 +9,10 @@
 // so every cluster gets the same number of units (+-1) over the chain, and a unit starts as soon as the 3 x 3 neighbourhood
 // of tile pairs it reads has been written by the previous layer — tile-level dataflow through per-unit counters in global
 // memory instead of a grid-wide barrier between layers:
-//   * epilogue warps: after the unit's activation stores, __syncwarp + one `red.release.gpu` on flag[layer][pair]
-//     (8 arrivals per unit: 4 epilogue warps x 2 CTAs);
+//   * epilogue warps: after the unit's activation stores, __syncwarp + one CTA-scope release arrive on a shared-memory
+//     mbarrier; a dedicated publisher warp per CTA waits on it and does the GPU-scope `red.release.gpu` (+4) on
+//     flag[layer][pair], so the MEMBAR.ALL.GPU that waits for the stores' acknowledgements is off the epilogue's critical
+//     path (first version, release in the epilogue warps: ncu stall_membar = 20 % of all samples, tensor pipe 33 % busy);
 //   * TMA producer warp: before the unit's loads, up to nine lanes poll (`ld.acquire.gpu`) the flags of the neighbouring
 //     pairs of the previous layer, then `fence.proxy.async` (the tiles were written through the generic proxy by other SMs
 //     and are read through the async proxy) and the two plane loads.
@@ -31,18 +33,30 @@ namespace chain {
 using namespace two;
 
 constexpr int kSlotsC = 3;
+constexpr int kEpiWarpsC = 8;                                         // two warps per TMEM lane quarter, 32 of the 64 channels each
+constexpr int kPubWarpC = 2 + kEpiWarpsC;
+constexpr int kThreadsC = 32 * (kPubWarpC + 1);                       // producer, MMA / weight forwarder, 8 epilogue warps, publisher
+constexpr int kMaxLayersC = kChainMaxLayers;
 constexpr uint32_t kOffAC = 2 * kWHalf;                               // after the two weight buffers
 constexpr uint32_t kOffBarC = kOffAC + kSlotsC * kPlaneSlot;
-constexpr uint32_t kSmemBytesC = kOffBarC + 256 + 1024;               // + slack for the manual 1024-B alignment
+constexpr uint32_t kOffBiasC = kOffBarC + 256;                        // bias[nlayers][64] + lo_scale[nlayers] of the whole chain
+constexpr uint32_t kSmemBytesC = kOffBiasC + kMaxLayersC * (256 + 4) + 1024;   // + slack for the manual 1024-B alignment
 constexpr int kAccStagesC = 4;
+constexpr int kDoneRing = 8;
+constexpr int kTraceClusters = 4, kTraceUnits = 64;
+// event slots of the debug timeline
+enum { TR_POLLED = 0, TR_TMA = 1, TR_TEMPTY = 2, TR_FULL0 = 3, TR_ISSUED = 4, TR_TFULL = 5, TR_STORED = 6, TR_PUBLISHED = 7 };
 static_assert(kSmemBytesC <= 227 * 1024, "chain kernel shared memory");
 
 struct ChainArgs {
   const ChainLayer* layers;   // device table [nlayers]
-  __half* act[2];
+  __half* act0;
+  __half* act1;
   uint32_t* flags;            // [nlayers][flag_stride]
   uint32_t target;            // 8 * epoch of this launch
   int flag_stride;
+  int interleave;             // MMA issue order: 0 = plane 0 then plane 1, 1 = the two kinds alternating (both planes first)
+  unsigned long long* trace;  // debug (pds_debug_chain_trace): [kTraceClusters][kTraceUnits][8] globaltimer stamps of CTA 0 of the first clusters
   int in_buf;                 // buffer read by chain layer 0
   int nlayers;
   float slope;
@@ -54,10 +68,26 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release_gpu_inc(uint32_t* p) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(1u) : "memory");
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// global state space only (FENCE.VIEW.ASYNC.G).  The unqualified form is MEMBAR.ALL.GPU + FENCE.VIEW.ASYNC.S: it also waits for
+// the TMA writes into shared memory that the producer has in flight — measured at 1.1 us per unit on the producer's critical path.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+__device__ __forceinline__ void trace_stamp(const ChainArgs& a, uint32_t rank, int cid, int k, int ev) {
+  if (a.trace != nullptr && rank == 0 && cid < kTraceClusters && k < kTraceUnits)
+    a.trace[((size_t)cid * kTraceUnits + k) * 8 + ev] = (unsigned long long)clock64();   // SM cycle counter: all stamps come from CTA 0's SM
+}
 
 // first layer > l among the units u = cid + k * nclusters of this cluster (-1: none)
 __device__ __forceinline__ int next_layer_of_cluster(int l, int cid, int nclusters, int npairs, int nunits) {
@@ -68,7 +98,7 @@ __device__ __forceinline__ int next_layer_of_cluster(int l, int cid, int ncluste
   return u < nunits ? u / npairs : -1;
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsC, 1)
     conv_chain_kernel(const __grid_constant__ CUtensorMap tmap0, const __grid_constant__ CUtensorMap tmap1, ChainArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -76,9 +106,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t sW = base, sA = base + kOffAC, sBar = base + kOffBarC;
   // barriers: full[3] @0 (CTA 0), empty[3] @24, tfull[4] @48, tempty[4] @80 (CTA 0), wfull[2] @112, wpeer[2] @128 (CTA 0),
-  // wempty[2] @144, tmem slot @160
+  // wempty[2] @144, tmem slot @160, done[8] @168 (epilogue -> publisher), publisher progress counter @232
   const uint32_t bFull = sBar, bEmpty = sBar + 24, bTFull = sBar + 48, bTEmpty = sBar + 80;
   const uint32_t bWFull = sBar + 112, bWPeer = sBar + 128, bWEmpty = sBar + 144, sTmemSlot = sBar + 160;
+  const uint32_t bDone = sBar + 168, sPubCount = sBar + 232;
+  float* bias_all = reinterpret_cast<float*>(gbase + kOffBiasC);             // [nlayers][64]
+  float* lo_all = bias_all + a.nlayers * 64;                                 // [nlayers]
   const uint32_t rank = cluster_rank();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -89,17 +122,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < kAccStagesC; ++i) {
       mbar_init(bTFull + 8 * i, 1);
-      mbar_init(bTEmpty + 8 * i, 8);        // 4 epilogue warps x 2 CTAs arrive on CTA 0's barrier
+      mbar_init(bTEmpty + 8 * i, 2 * kEpiWarpsC);   // the epilogue warps of both CTAs arrive on CTA 0's barrier
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bWFull + 8 * i, 1);         // own half of a layer's weight image landed
       mbar_init(bWPeer + 8 * i, 1);         // CTA 0: the peer's half landed too
       mbar_init(bWEmpty + 8 * i, 1);        // every MMA that read this weight buffer has completed (multicast commit)
     }
+    for (int i = 0; i < kDoneRing; ++i) mbar_init(bDone + 8 * i, kEpiWarpsC);   // this CTA's epilogue warps stored their part of a unit
+    sts_volatile(sPubCount, 0u);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap1) : "memory");
   }
+  // biases / correction scales of every layer of the chain (constants: no dependence on the previous grid)
+  for (int i = threadIdx.x; i < a.nlayers * 64; i += kThreadsC) bias_all[i] = __ldg(a.layers[i >> 6].bias + (i & 63));
+  for (int i = threadIdx.x; i < a.nlayers; i += kThreadsC) lo_all[i] = a.layers[i].lo_scale;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(kTmemCols2) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -120,8 +158,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     // ------------------------------------------------------------ producer: dependencies, activation planes, weights
     pdl_wait_prior_grid();
     uint32_t j = 0;
-    int gen = -1, issued = -1, prev_l = -1;
-    for (int u = cid; u < nunits; u += nclusters) {
+    int gen = -1, issued = -1, prev_l = -1, kk = 0;
+    for (int u = cid; u < nunits; u += nclusters, ++kk) {
       const int l = u / npairs, p = u - l * npairs;
       const bool first_of_gen = l != prev_l;
       if (first_of_gen) ++gen;
@@ -148,8 +186,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
         __syncwarp();
-        fence_proxy_async();                // generic-proxy writes of other SMs (acquired above) -> async-proxy TMA reads below
+        fence_proxy_async_global();         // generic-proxy writes of other SMs (acquired above) -> async-proxy TMA reads below
       }
+      if (lane == 0) trace_stamp(a, rank, cid, kk, TR_POLLED);
       // 2. first plane slot of the unit (all MMAs of unit k-2 have completed once this passes)
       mbar_wait(bEmpty + 8 * (j % kSlotsC), ((j / kSlotsC) & 1) ^ 1);
       // 3. weights: this generation must be on its way; from the second unit of a generation on, fetch the next layer's image
@@ -183,6 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         }
         __syncwarp();
       }
+      if (lane == 0) trace_stamp(a, rank, cid, kk, TR_TMA);
     }
   } else if (warp == 1) {
     if (rank == 0) {
@@ -205,24 +245,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         const uint32_t w_lo = (((sW + wbuf * kWHalf) & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t acc = it % kAccStagesC;
         mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it / kAccStagesC) & 1) ^ 1));
+        if (lane == 0) trace_stamp(a, rank, cid, it, TR_TEMPTY);
         const uint32_t d_tmem = tmem_base + acc * kAccCols2;
-#pragma unroll
-        for (int pl = 0; pl < 2; ++pl, ++j) {
-          const uint32_t slot = j % kSlotsC, use = j / kSlotsC;
-          mbar_wait(bFull + 8 * slot, use & 1);
+        if (a.interleave == 1) {
+          // both planes first, then the two MMA kinds alternating (independent accumulators)
+          const uint32_t s0 = j % kSlotsC, u0 = j / kSlotsC, s1 = (j + 1) % kSlotsC, u1 = (j + 1) / kSlotsC;
+          mbar_wait(bFull + 8 * s0, u0 & 1);
+          if (lane == 0) trace_stamp(a, rank, cid, it, TR_FULL0);
+          mbar_wait(bFull + 8 * s1, u1 & 1);
           tc_fence_after();
-          const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t a0_lo = (((sA + s0 * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t a1_lo = (((sA + s1 * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
           if (elect_one()) {
-            if (pl == 0) issue_plane2<true>(d_tmem, a_lo, w_lo);
-            else issue_plane2<false>(d_tmem, a_lo, w_lo);
-            umma_commit_2sm(bEmpty + 8 * slot);
-            if (pl == 1) {
-              umma_commit_2sm(bTFull + 8 * acc);
-              if (last_of_gen) umma_commit_2sm(bWEmpty + 8 * wbuf);
-            }
+            issue_unit2_interleaved(d_tmem, a0_lo, a1_lo, w_lo);
+            umma_commit_2sm(bEmpty + 8 * s0);
+            umma_commit_2sm(bEmpty + 8 * s1);
+            umma_commit_2sm(bTFull + 8 * acc);
+            if (last_of_gen) umma_commit_2sm(bWEmpty + 8 * wbuf);
           }
           __syncwarp();
+          j += 2;
+        } else {
+#pragma unroll
+          for (int pl = 0; pl < 2; ++pl, ++j) {
+            const uint32_t slot = j % kSlotsC, use = j / kSlotsC;
+            mbar_wait(bFull + 8 * slot, use & 1);
+            tc_fence_after();
+            if (pl == 0 && lane == 0) trace_stamp(a, rank, cid, it, TR_FULL0);
+            const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+            if (elect_one()) {
+              if (a.interleave == 2) {            // timing probe (wrong results): A from the collector, see tc_common.cuh
+                if (pl == 0) issue_plane2_probe_collector<true>(d_tmem, a_lo, w_lo);
+                else issue_plane2_probe_collector<false>(d_tmem, a_lo, w_lo);
+              } else if (pl == 0) issue_plane2<true>(d_tmem, a_lo, w_lo);
+              else issue_plane2<false>(d_tmem, a_lo, w_lo);
+              umma_commit_2sm(bEmpty + 8 * slot);
+              if (pl == 1) {
+                umma_commit_2sm(bTFull + 8 * acc);
+                if (last_of_gen) umma_commit_2sm(bWEmpty + 8 * wbuf);
+              }
+            }
+            __syncwarp();
+          }
         }
+        if (lane == 0) trace_stamp(a, rank, cid, it, TR_ISSUED);
       }
     } else {
       // ------------------------------------------------------------ CTA 1: tell the MMA issuer when this half of a weight image landed
@@ -239,9 +305,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
         if (lane == 0) mbar_arrive_cluster(map_to_cta(bWPeer + 8 * wbuf, 0));
       }
     }
+  } else if (warp == kPubWarpC) {
+    // ------------------------------------------------------------ publisher: GPU-scope release of finished units
+    int it = 0;
+    for (int u = cid; u < nunits; u += nclusters, ++it) {
+      const int l = u / npairs, p = u - l * npairs;
+      mbar_wait(bDone + 8 * (it & (kDoneRing - 1)), (uint32_t)((it / kDoneRing) & 1));   // acquire.cta: the epilogue warps' stores
+      if (lane == 0) {
+        red_release_gpu_add(a.flags + (size_t)l * a.flag_stride + p, 4u);                // cumulative: release.gpu over what was acquired
+        sts_volatile(sPubCount, (uint32_t)(it + 1));
+        trace_stamp(a, rank, cid, it, TR_PUBLISHED);
+      }
+      __syncwarp();
+    }
   } else {
     // ------------------------------------------------------------ epilogue (each CTA drains its own 128 TMEM lanes)
-    const int q = warp & 3;
+    // The steady state of the chain has no per-layer tail to hide a slow epilogue in (a per-layer launch runs its <= 4 units
+    // into the 4 TMEM stages and drains them while the next launch sets up): with four warps the epilogue took 2.2 us per unit
+    // against 1.6 us of MMAs (ncu: epilogue warps 80 % busy, tensor pipe 43 %).  Eight warps: each drains 32 of the 64 channels.
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;         // channels [32 half, 32 half + 32)
     const int m = q * 32 + lane;
     const int ty = m >> 3, tx = m & 7;
     const size_t hw = (size_t)a.H * a.W;
@@ -254,32 +337,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int tl = live ? tile : a.ntiles - 1;
       const int img = tl / per_img, rem = tl - img * per_img;
       const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
-      const float* bias = a.layers[l].bias;
-      const float lo_scale = a.layers[l].lo_scale;
-      __half* outb = a.act[(a.in_buf + l + 1) & 1];
+      const float* bias = bias_all + l * 64;
+      const float lo_scale = lo_all[l];
+      __half* outb = ((a.in_buf + l + 1) & 1) ? a.act1 : a.act0;
       const uint32_t acc = it % kAccStagesC;
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it / kAccStagesC) & 1));
       tc_fence_after();
+      if (warp == 2 && lane == 0) trace_stamp(a, rank, cid, it, TR_TFULL);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols2;
       const bool st = live && y < a.H && x < a.W;
       const size_t pix = (size_t)y * a.W + x;
       __half* o_p0 = outb + (((size_t)img * 2 + 0) * hw + pix) * 64;
       uint8_t* o_p1 = reinterpret_cast<uint8_t*>(outb + (((size_t)img * 2 + 1) * hw + pix) * 64);
-      uint32_t r0[32], r1[32], r2[32], r3[32];
-      tmem_ld32(taddr + 0, r0);
-      tmem_ld32(taddr + 64, r2);
-      tmem_ld32(taddr + 32, r1);
-      tmem_ld32(taddr + 96, r3);
+      uint32_t r0[32], r2[32];
+      tmem_ld32(taddr + 32 * half, r0);       // a_hi * w_hi accumulator
+      tmem_ld32(taddr + 64 + 32 * half, r2);  // e4m3 correction accumulator
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * acc);      // stage released before any arithmetic or store
-      if (st) {
-        store_half_row(o_p0, o_p1, r0, r2, bias, 0, a.slope, lo_scale, 1);
-        store_half_row(o_p0, o_p1, r1, r3, bias, 32, a.slope, lo_scale, 1);
-      }
+      if (st) store_half_row(o_p0, o_p1, r0, r2, bias, 32 * half, a.slope, lo_scale, 1);
       __syncwarp();
-      if (lane == 0) red_release_gpu_inc(a.flags + (size_t)l * a.flag_stride + p);   // cumulative over the warp's stores
+      if (warp == 2 && lane == 0) trace_stamp(a, rank, cid, it, TR_STORED);
+      if (lane == 0) {
+        // ring-slot reuse: the publisher has consumed this slot's previous phase (it never lags 8 units in practice)
+        while (it >= kDoneRing && (int)lds_volatile(sPubCount) < it - (kDoneRing - 1)) {}
+        mbar_arrive(bDone + 8 * (it & (kDoneRing - 1)));     // release.cta, cumulative over the warp's stores (after __syncwarp)
+      }
     }
   }
   tc_fence_before();
@@ -307,7 +391,7 @@ int chain_setup() {
 int tc_plan_set_chain(TcPlan* plan, const std::vector<ChainLayer>& layers) {
   const int tiles = ((plan->W + kTileCols - 1) / kTileCols) * ((plan->H + kTileRows - 1) / kTileRows) * plan->nimg;
   const int npairs = (tiles + 1) / 2;
-  if (layers.empty() || npairs > kChainMaxPairs) return 0;            // launches this large use the per-layer kernels
+  if (layers.empty() || npairs > kChainMaxPairs || (int)layers.size() > kChainMaxLayers) return 0;   // -> per-layer kernels
   PDS_CUDA_OK(cudaMalloc(&plan->chain_layers, layers.size() * sizeof(ChainLayer)));
   PDS_CUDA_OK(cudaMemcpy(plan->chain_layers, layers.data(), layers.size() * sizeof(ChainLayer), cudaMemcpyHostToDevice));
   const size_t nflags = layers.size() * (size_t)npairs;
@@ -327,13 +411,15 @@ bool chain_available(const TcPlan* plan, int nimg) {
   return (tiles + 1) / 2 <= plan->chain_stride;
 }
 
-cudaError_t launch_conv_chain(TcPlan* plan, int in_buf, int nimg, float slope, cudaStream_t st) {
+cudaError_t launch_conv_chain(TcPlan* plan, int in_buf, int nimg, float slope, int interleave, cudaStream_t st) {
   chain::ChainArgs a{};
+  a.interleave = interleave;
   a.layers = plan->chain_layers;
-  a.act[0] = plan->act[0];
-  a.act[1] = plan->act[1];
+  a.act0 = plan->act[0];
+  a.act1 = plan->act[1];
   a.flags = plan->chain_flags;
   a.flag_stride = plan->chain_stride;
+  a.trace = plan->chain_trace;
   a.in_buf = in_buf;
   a.nlayers = plan->chain_nlayers;
   a.slope = slope;
@@ -356,7 +442,24 @@ cudaError_t launch_conv_chain(TcPlan* plan, int in_buf, int nimg, float slope, c
   const int nunits = a.nlayers * a.npairs;
   const int half = plan->num_sms / 2;
   const int nclusters = nunits < half ? nunits : half;
-  return launch_pdl(chain::conv_chain_kernel, 2 * nclusters, kThreads, chain::kSmemBytesC, st, plan->map[0], plan->map[1], a);
+  return launch_pdl(chain::conv_chain_kernel, 2 * nclusters, chain::kThreadsC, chain::kSmemBytesC, st, plan->map[0], plan->map[1], a);
+}
+
+// Debug timeline (pds_debug_chain_trace): arm -> the next chain launches stamp the SM cycle counter at the pipeline events of the first
+// units of the first clusters; read -> copies the stamps back and disarms.
+int tc_chain_trace(TcPlan* plan, unsigned long long* out_host) {
+  const size_t n = (size_t)chain::kTraceClusters * chain::kTraceUnits * 8;
+  if (out_host == nullptr) {
+    if (!plan->chain_trace) PDS_CUDA_OK(cudaMalloc(&plan->chain_trace, n * sizeof(unsigned long long)));
+    PDS_CUDA_OK(cudaMemset(plan->chain_trace, 0, n * sizeof(unsigned long long)));
+    return 0;
+  }
+  PDS_REQUIRE(plan->chain_trace != nullptr, "chain trace is not armed");
+  PDS_CUDA_OK(cudaDeviceSynchronize());
+  PDS_CUDA_OK(cudaMemcpy(out_host, plan->chain_trace, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  cudaFree(plan->chain_trace);
+  plan->chain_trace = nullptr;
+  return 0;
 }
 
 // ---- interface used by pds_api.cu (kernels.cuh) ----
@@ -368,8 +471,8 @@ int tc_plan_chain(TcPlan* plan, const DncnnLayerW* layers, int depth, size_t* by
   return rc;
 }
 bool tc_chain_available(const TcPlan* plan, int nimg) { return chain_available(plan, nimg); }
-cudaError_t launch_conv_body_chain(TcPlan* plan, int in_buf, int nimg, float slope, cudaStream_t st) {
-  return launch_conv_chain(plan, in_buf, nimg, slope, st);
+cudaError_t launch_conv_body_chain(TcPlan* plan, int in_buf, int nimg, float slope, int interleave, cudaStream_t st) {
+  return launch_conv_chain(plan, in_buf, nimg, slope, interleave, st);
 }
 
 }  // namespace pds

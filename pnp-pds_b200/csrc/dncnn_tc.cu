@@ -949,6 +949,7 @@ void tc_plan_destroy(TcPlan* p) {
   if (!p) return;
   if (p->chain_layers) cudaFree(p->chain_layers);
   if (p->chain_flags) cudaFree(p->chain_flags);
+  if (p->chain_trace) cudaFree(p->chain_trace);
   delete p;
 }
 

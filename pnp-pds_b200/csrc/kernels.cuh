@@ -125,7 +125,8 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
 // all body layers in one persistent launch (dncnn_chain.cu); set up by tc_plan_chain after the layers are uploaded
 int tc_plan_chain(TcPlan* plan, const DncnnLayerW* layers, int depth, size_t* bytes_out);
 bool tc_chain_available(const TcPlan* plan, int nimg);
-cudaError_t launch_conv_body_chain(TcPlan* plan, int in_buf, int nimg, float slope, cudaStream_t st);
+cudaError_t launch_conv_body_chain(TcPlan* plan, int in_buf, int nimg, float slope, int interleave, cudaStream_t st);
+int tc_chain_trace(TcPlan* plan, unsigned long long* out_host);   // debug timeline: null = arm, else read back [4][64][8] and disarm
 int tc_num_sms();
 // row-streaming body layer (dncnn_roll.cu): band height for a launch of nimg images (0 = not applicable, use the tile kernels)
 int roll_setup();

@@ -231,7 +231,7 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const bool chain = h->conv_engine == PDS_CONV_TCGEN05 && band == 0 && two_cta && !(h->tc_variant & 512) && h->depth > 2 &&
                        tc_chain_available(h->tc, nimg);
     if (chain) {
-      PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_body_chain(h->tc, src, nimg, h->slope, st));
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_body_chain(h->tc, src, nimg, h->slope, (h->tc_variant & 4096) ? 2 : ((h->tc_variant & 2048) ? 1 : 0), st));
       src ^= (h->depth - 2) & 1;
     }
     for (int l = 1; l < h->depth - 1 && !chain; ++l) {
@@ -1076,6 +1076,13 @@ int pds_debug_set_conv_engine(pds_handle_t h, int engine) {
   PDS_REQUIRE(!h->have_net, "pds_debug_set_conv_engine must precede pds_load_dncnn");
   h->conv_engine = engine;
   return 0;
+}
+
+/* test hook: %globaltimer timeline of the chain kernel's pipeline events (tools/chain_timeline.py) */
+int pds_debug_chain_trace(pds_handle_t h, unsigned long long* out_host) {
+  PDS_TRY(check_handle(h));
+  PDS_REQUIRE(h->tc != nullptr, "no tcgen05 plan (pds_load_dncnn first)");
+  return tc_chain_trace(h->tc, out_host);
 }
 
 /* test hook: perf-experiment switches of the tcgen05 engine (see run_dncnn) */

@@ -18,6 +18,7 @@ struct ChainLayer {
   float lo_scale;
   float pad;
 };
+constexpr int kChainMaxLayers = 40;     // biases of the whole chain are staged in shared memory (reference networks: 15 / 18 body layers)
 constexpr int kChainMaxPairs = 16384;   // launches of up to 2 Mpx can run as one chain launch (flags: layers x pairs x 4 B)
 
 // Tensor maps and geometry of the two activation buffers of one engine handle.
@@ -33,11 +34,12 @@ struct TcPlan {
   int chain_nlayers = 0, chain_stride = 0, chain_npairs_last = -1;
   uint32_t chain_epoch = 0;
   size_t chain_bytes = 0;
+  unsigned long long* chain_trace = nullptr;   // debug timeline buffer (pds_debug_chain_trace), normally null
 };
 int chain_setup();
 int tc_plan_set_chain(TcPlan* plan, const std::vector<ChainLayer>& layers);
 bool chain_available(const TcPlan* plan, int nimg);
-cudaError_t launch_conv_chain(TcPlan* plan, int in_buf, int nimg, float slope, cudaStream_t st);
+cudaError_t launch_conv_chain(TcPlan* plan, int in_buf, int nimg, float slope, int interleave, cudaStream_t st);
 
 namespace {
 
@@ -332,6 +334,45 @@ __device__ __forceinline__ void issue_plane2(uint32_t d_tmem, uint32_t a_lo, uin
       const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
       if (P0) umma_f16_2sm(d_tmem, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
       else umma_f8_2sm(d_tmem + 64u, desc64(a_lo + ao, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
+    }
+  }
+}
+// Both planes of a unit, the two MMA kinds alternating: consecutive MMAs then accumulate into DIFFERENT TMEM accumulators
+// (f16 -> columns [0,64), f8f6f4 -> [64,128)), so an MMA does not wait for its predecessor's accumulator update.  The order of
+// the MMAs within each accumulator is that of issue_plane2 -> bit-identical results.
+__device__ __forceinline__ void issue_unit2_interleaved(uint32_t d_tmem, uint32_t a0_lo, uint32_t a1_lo, uint32_t w_lo) {
+  constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);
+  constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap - dy * 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t ao = (uint32_t)((dy * kHaloPitch + dx) * 128 + k * 32) >> 4;
+      const uint32_t b0 = (uint32_t)(tap * 8192 + k * 32) >> 4;
+      const uint32_t b1 = (uint32_t)(tap * 8192 + 4096 + k * 32) >> 4;
+      const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
+      umma_f16_2sm(d_tmem, desc64(a0_lo + ao, kHiA), desc64(w_lo + b0, kHiB), kIdescN64, acc);
+      umma_f8_2sm(d_tmem + 64u, desc64(a1_lo + ao, kHiA), desc64(w_lo + b1, kHiB), kIdescN64, acc);
+    }
+  }
+}
+// TIMING PROBE ONLY (wrong results): every MMA of the plane reads the SAME A tile and keeps it in the collector, so shared memory
+// only delivers the B operand.  Separates "bound by shared-memory operand reads" from "bound by MMA issue" (tools/chain_timeline.py).
+template <bool P0>
+__device__ __forceinline__ void issue_plane2_probe_collector(uint32_t d_tmem, uint32_t a_lo, uint32_t w_lo) {
+  constexpr uint32_t kHiA = ((kHaloPitch * 128u) >> 4) | (1u << 14) | (2u << 29);
+  constexpr uint32_t kHiB = (1024u >> 4) | (1u << 14) | (2u << 29);
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t bo = (uint32_t)(tap * 8192 + (P0 ? 0 : 4096) + k * 32) >> 4;
+      const uint32_t acc = (tap == 0 && k == 0) ? 0u : 1u;
+      const bool first = tap == 0 && k == 0, last = tap == 8 && k == 3;
+      if (first) umma_2sm<P0, 1>(d_tmem + (P0 ? 0u : 64u), desc64(a_lo, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
+      else if (last) umma_2sm<P0, 3>(d_tmem + (P0 ? 0u : 64u), desc64(a_lo, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
+      else umma_2sm<P0, 2>(d_tmem + (P0 ? 0u : 64u), desc64(a_lo, kHiA), desc64(w_lo + bo, kHiB), kIdescN64, acc);
     }
   }
 }
