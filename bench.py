@@ -369,6 +369,7 @@ def main():
     eng.load_dncnn(weights)
     if a.tc_variant:
         eng.set_tc_variant(a.tc_variant)
+    body_kernel_code = eng.body_kernel()
 
     # ---- device-resident timing: inputs already in HBM when the timed region starts
     eng.set_problem(h_x0.to(dev, non_blocking=True), h_obs.to(dev, non_blocking=True), h_true.to(dev, non_blocking=True))
@@ -470,23 +471,21 @@ def main():
         n_mid_layers = weights.depth - 2
         # which body-layer kernel the library dispatches for this launch shape (pds_api.cu run_dncnn)
         mid_bytes_px = 512.0                 # body layer: read + write [fp16 x 64 | e4m3(a) x 64 | e4m3(a_lo) x 64] per pixel
-        if a.engine != "tcgen05":
-            mid_kernel = "conv_mid_simt_kernel"
-        elif eng.lib.pds_debug_roll_band_rows(int(chunk), H, W, 0) > 0:
-            hbm = bool(a.tc_variant & 256)
-            mid_kernel = ("roll::conv_roll_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand read from HBM)" if hbm else
-                          "roll::conv_roll_d_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand rebuilt on chip from the fp16 row)")
-            if not hbm:                      # e4m3(a) neither stored nor read, except the store of the layer feeding the last one
+        bk = body_kernel_code
+        mid_kernel = Engine.BODY_KERNELS.get(bk, "?")
+        if bk == 1:
+            if a.tc_variant & 256:
+                mid_kernel = "roll::conv_roll_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand read from HBM)"
+            else:                            # e4m3(a) neither stored nor read, except the store of the layer feeding the last one
                 mid_bytes_px = 384.0 + 64.0 / n_mid_layers
-        else:
-            mid_kernel = "two::conv_tc2_kernel (cta_group::2 tile kernel)"
+        launches_per_pass = 1 if bk == 4 else n_mid_layers
         total_flop = DNCNN_FLOP_PER_PX_MID_LAYER * float(B * H * W) * n_mid_layers * a.steps
         achieved = total_flop / (mid_ms * 1e-3) / 1e12 if mid_n else None
         # DRAM traffic of the body-layer kernel per launch, from the committed ncu --set full capture (bytes per pixel x
         # pixels per launch); only claimed for the shape it was captured on
         traffic = None
         tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if a.engine == "tcgen05" and a.workload == "cfg4" and os.path.exists(tj):
+        if bk == 1 and not (a.tc_variant & 256) and a.workload == "cfg4" and os.path.exists(tj):
             traffic = json.load(open(tj))["bytes_per_px"] * chunk * H * W
         dual_ms, dual_n = prof["dual"]
         prim_ms, prim_n = prof["primal"]
@@ -514,9 +513,10 @@ def main():
                      parts_rank0={k: float(v) for k, v in e2e_parts.items()}, api=e2e_api),
             roofline=dict(bound="tensor", kernel=mid_kernel,
                           achieved=achieved, peak=pk["tensor"], unit="TFLOP/s", frac=(achieved / pk["tensor"]) if achieved else None,
+                          layers_per_launch=(n_mid_layers if bk == 4 else 1),
                           traffic=traffic, traffic_source=("ncu --set full capture of this kernel at this launch shape, committed under profiles/ "
                                                            "(ncu_traffic.json names the capture); not re-measured in this run") if traffic else None,
-                          algorithmic_bytes_per_launch=mid_bytes_px * chunk * H * W,
+                          algorithmic_bytes_per_launch=mid_bytes_px * chunk * H * W * (n_mid_layers if bk == 4 else 1),
                           issued_tflops_fp16_equiv=(2.0 * achieved) if (achieved and a.engine == "tcgen05") else None,
                           peak_source=pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
                           launches=int(mid_n), avg_ms=mid_ms / max(1, mid_n),

@@ -176,6 +176,10 @@ int pds_debug_set_tc_variant(pds_handle_t h, int variant);
  * plane landed, MMAs issued, accumulator ready, stored, published) for the first 64 units of CTA 0 of the first 4 clusters:
  * out_host == NULL arms the trace for the following launches, otherwise [4][64][8] uint64 are copied back and it is disarmed */
 int pds_debug_chain_trace(pds_handle_t h, unsigned long long* out_host);
+/* which kernel serves the 64->64 body layers of a launch of nimg images (nimg <= 0: a full denoiser chunk) on this handle:
+ * 0 fp32 CUDA-core engine, 1 row-streaming, 2 CTA-pair tile kernel per layer, 3 1-CTA tile kernel per layer, 4 chain kernel
+ * (all body layers in one persistent launch); -1 before pds_load_dncnn */
+int pds_debug_body_kernel(pds_handle_t h, int nimg);
 /* rows per CTA pair when the row-streaming body kernels serve a launch of nimg images of H x W on the current device;
  * 0 = the tile kernels run instead (narrower than 128 pixels, or the cost model prefers tiles; force != 0 skips that comparison) */
 int pds_debug_roll_band_rows(int nimg, int H, int W, int force);

@@ -65,6 +65,7 @@ def _declare(lib):
         "pds_debug_set_tc_variant": (i, [vp, i]),
         "pds_debug_set_conv_engine": (i, [vp, i]),
         "pds_debug_chain_trace": (i, [vp, vp]),
+        "pds_debug_body_kernel": (i, [vp, i]),
         "pds_debug_roll_band_rows": (i, [i, i, i, i]),
         "pds_debug_umma_probe": (i, [u, u, u, u, vp]),
         "pds_debug_tma_probe": (i, [vp, i, i, i, i, i, i, vp]),

@@ -203,6 +203,22 @@ int apply_phi(pds_handle_s* h, bool adjoint, const float* in, float* out, cudaSt
   PDS_REQUIRE(false, "unknown deg_op");
 }
 
+// Which kernel serves the 64->64 body layers of a launch of nimg images (see run_dncnn for the switches in tc_variant).
+struct BodyDispatch {
+  int band;        // > 0: row-streaming kernel with this band height
+  bool two_cta;    // tile kernels: CTA-pair form
+  bool chain;      // all body layers in one persistent launch (dncnn_chain.cu)
+};
+BodyDispatch body_dispatch(const pds_handle_s* h, int nimg) {
+  BodyDispatch b{};
+  const Dims& d = h->d;
+  b.band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
+  b.two_cta = !(h->tc_variant & 16);
+  b.chain = h->conv_engine == PDS_CONV_TCGEN05 && b.band == 0 && b.two_cta && !(h->tc_variant & 512) && h->depth > 2 && h->tc &&
+            tc_chain_available(h->tc, nimg);
+  return b;
+}
+
 // Denoiser.denoise over all B items, `chunk` images per pass so that activations can stay in L2.
 int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
   PDS_REQUIRE(h->have_net, "denoiser weights not loaded (pds_load_dncnn)");
@@ -217,8 +233,9 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     // kernel stays as a cross-check.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width
     // allows, bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel, bit 8 makes the row-streaming kernel read e4m3(a) from
     // HBM instead of rebuilding it on chip (then every layer stores it).
-    const int band = (h->tc_variant & (128 | 32 | 16)) ? 0 : roll_band_rows(nimg, d.H, d.W, tc_num_sms_cached(), (h->tc_variant & 64) != 0);
-    const bool two_cta = !(h->tc_variant & 16);
+    const BodyDispatch bd = body_dispatch(h, nimg);
+    const int band = bd.band;
+    const bool two_cta = bd.two_cta;
     const bool derive = band > 0 && !(h->tc_variant & 256);
     if (h->conv_engine == PDS_CONV_TCGEN05) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, derive ? 0 : 1, st));
@@ -228,8 +245,7 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     int src = 0;
     // small launches (the tile kernels' territory): all body layers in ONE persistent launch with tile-level dataflow between
     // layers (dncnn_chain.cu).  tc_variant bit 9 disables it (per-layer tile kernels: the bit-exact cross-check).
-    const bool chain = h->conv_engine == PDS_CONV_TCGEN05 && band == 0 && two_cta && !(h->tc_variant & 512) && h->depth > 2 &&
-                       tc_chain_available(h->tc, nimg);
+    const bool chain = bd.chain;
     if (chain) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_body_chain(h->tc, src, nimg, h->slope, (h->tc_variant & 4096) ? 2 : ((h->tc_variant & 2048) ? 1 : 0), st));
       src ^= (h->depth - 2) & 1;
@@ -1083,6 +1099,18 @@ int pds_debug_chain_trace(pds_handle_t h, unsigned long long* out_host) {
   PDS_TRY(check_handle(h));
   PDS_REQUIRE(h->tc != nullptr, "no tcgen05 plan (pds_load_dncnn first)");
   return tc_chain_trace(h->tc, out_host);
+}
+
+/* test hook: which kernel serves the body layers of a launch of nimg images: 0 fp32 CUDA-core engine, 1 row-streaming
+ * (conv_roll_d_kernel / conv_roll_kernel), 2 CTA-pair tiles (conv_tc2_kernel), 3 1-CTA tiles (conv_tc_kernel), 4 chain kernel */
+int pds_debug_body_kernel(pds_handle_t h, int nimg) {
+  if (!h || !h->have_net) return -1;
+  if (h->conv_engine != PDS_CONV_TCGEN05) return 0;
+  if (nimg <= 0 || nimg > h->chunk) nimg = h->chunk;
+  const BodyDispatch b = body_dispatch(h, nimg);
+  if (b.band > 0) return 1;
+  if (b.chain) return 4;
+  return b.two_cta ? 2 : 3;
 }
 
 /* test hook: perf-experiment switches of the tcgen05 engine (see run_dncnn) */

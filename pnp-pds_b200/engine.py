@@ -145,6 +145,16 @@ class Engine:
         buf = C.create_string_buffer(blob, len(blob))
         _lib.check(self.lib.pds_load_dncnn(self._h, C.cast(buf, C.c_void_p), len(blob)))
 
+    BODY_KERNELS = {0: "conv_mid_simt_kernel (fp32 CUDA-core cross-check engine)",
+                    1: "roll::conv_roll_d_kernel (row-streaming cta_group::2 body layer, e4m3(a) operand rebuilt on chip from the fp16 row)",
+                    2: "two::conv_tc2_kernel (cta_group::2 tile kernel, one launch per layer)",
+                    3: "conv_tc_kernel<64> (1-CTA tile kernel, one launch per layer)",
+                    4: "chain::conv_chain_kernel (all body layers in one persistent cta_group::2 launch, tile-level dataflow between layers)"}
+
+    def body_kernel(self, nimg: int = 0) -> int:
+        """Which kernel serves the 64->64 body layers (pds_debug_body_kernel): key of BODY_KERNELS."""
+        return int(self.lib.pds_debug_body_kernel(self._h, int(nimg)))
+
     def set_tc_variant(self, v: int):
         _lib.check(self.lib.pds_debug_set_tc_variant(self._h, int(v)))
 
