@@ -160,6 +160,35 @@ long long pds_kernel_launches(pds_handle_t h);
 /* bytes of device workspace owned by the handle */
 size_t pds_workspace_bytes(pds_handle_t h);
 
+/* ---- KAIR UNet forward ----
+ * models/network_unet.py:13-66 (UNet: head, 3 x [nb convs + 2x2 stride-2 conv], nb+1 body convs, 3 x [2x2 stride-2 transposed
+ * conv + nb convs], tail; skip additions and the input residual), blocks of models/basicblock.py:61-63, 413-419, 439-445.
+ * The reference class cannot be constructed (load_state_dict before any layer exists, network_unet.py:17) and ships no weights;
+ * this is the forward operator for that architecture in exact fp32, with its own handle.  Images: fp32 planar (B, C, H, W),
+ * H and W divisible by 8. */
+typedef struct pds_unet_s* pds_unet_t;
+typedef struct {
+  int32_t batch;
+  int32_t in_nc;      /* UNet(in_nc=...) */
+  int32_t out_nc;     /* == in_nc (input residual, network_unet.py:62) */
+  int32_t nc[4];      /* channel widths of the four levels (reference default 64, 128, 256, 512) */
+  int32_t nb;         /* convs per level (reference default 2) */
+  int32_t height;
+  int32_t width;
+  int32_t device;
+} pds_unet_config_t;
+int pds_unet_create(const pds_unet_config_t* cfg, pds_unet_t* out);
+int pds_unet_destroy(pds_unet_t h);
+/* size of the PDSU weight blob for this configuration: 48-byte header ("PDSU", version 1, in_nc, out_nc, nc[4], nb) followed by,
+ * in module order (m_head, m_down1..3, m_body, m_up3..1, m_tail), each layer's weight in its torch layout (Conv2d
+ * [cout][cin][k][k], ConvTranspose2d [cin][cout][k][k]) and bias, fp32 */
+size_t pds_unet_blob_bytes(const pds_unet_config_t* cfg);
+int pds_unet_load(pds_unet_t h, const void* blob_host, size_t nbytes);
+/* UNet.forward (network_unet.py:52-64); device pointers, not in place */
+int pds_unet_forward(pds_unet_t h, const float* in_dev, float* out_dev, pds_stream_t stream);
+long long pds_unet_kernel_launches(pds_unet_t h);
+size_t pds_unet_workspace_bytes(pds_unet_t h);
+
 /* ---- test hooks (hardware probes used by tests/test_gpu_tcgen05.py; not part of the drop-in surface) ---- */
 /* The denoiser always runs on the tcgen05 engine (TMA-fed implicit GEMM: fp16 product + e4m3 operand corrections, fp32 TMEM
  * accumulators).  A fp32 CUDA-core direct convolution is kept as an on-device cross-check for the tests; it is selected per

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpnp_pds.so")
-SOURCES = ["pds_api.cu", "pds_elementwise.cu", "pds_blur.cu", "pds_l1ball.cu", "pds_ssim.cu", "pds_tv.cu", "dncnn_simt.cu", "dncnn_tc.cu", "dncnn_roll.cu", "dncnn_chain.cu"]
+SOURCES = ["pds_api.cu", "pds_elementwise.cu", "pds_blur.cu", "pds_l1ball.cu", "pds_ssim.cu", "pds_tv.cu", "dncnn_simt.cu", "dncnn_tc.cu", "dncnn_roll.cu", "dncnn_chain.cu", "unet.cu"]
 HEADERS = ["common.cuh", "kernels.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "pnp_pds.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "--use_fast_math=false"]

@@ -28,6 +28,11 @@ class PdsItemParams(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("gamma1", "gamma2", "epsilon", "eta", "lam", "alpha")]
 
 
+class PdsUnetConfig(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("in_nc", C.c_int32), ("out_nc", C.c_int32), ("nc", C.c_int32 * 4), ("nb", C.c_int32),
+                ("height", C.c_int32), ("width", C.c_int32), ("device", C.c_int32)]
+
+
 class PdsError(RuntimeError):
     pass
 
@@ -62,6 +67,13 @@ def _declare(lib):
         "pds_profile_read": (i, [vp, vp, vp, i, vp]),
         "pds_kernel_launches": (C.c_longlong, [vp]),
         "pds_workspace_bytes": (sz, [vp]),
+        "pds_unet_create": (i, [C.POINTER(PdsUnetConfig), C.POINTER(vp)]),
+        "pds_unet_destroy": (i, [vp]),
+        "pds_unet_blob_bytes": (sz, [C.POINTER(PdsUnetConfig)]),
+        "pds_unet_load": (i, [vp, vp, sz]),
+        "pds_unet_forward": (i, [vp, vp, vp, vp]),
+        "pds_unet_kernel_launches": (C.c_longlong, [vp]),
+        "pds_unet_workspace_bytes": (sz, [vp]),
         "pds_debug_set_tc_variant": (i, [vp, i]),
         "pds_debug_set_conv_engine": (i, [vp, i]),
         "pds_debug_chain_trace": (i, [vp, vp]),

@@ -263,6 +263,36 @@ def gen_base(ref, cases, only_tags=()):
         save(f"base_{case['tag']}.npz", **out)
 
 
+def gen_unet(ref):
+    """UNet.forward of the reference's own module graph (models/network_unet.py:13-66) for small channel widths.  The class
+    cannot be constructed as shipped (network_unet.py:17: load_state_dict(torch.load(file_name)) before any layer exists), so
+    exactly that statement is neutralised while __init__ runs; layers, forward and parameter names are the reference's."""
+    import torch
+    import models.network_unet as nu
+    out = {}
+    for tag, in_nc, nc, nb, hw in (("g", 1, [8, 16, 24, 32], 2, (24, 40)), ("c", 3, [16, 16, 32, 40], 2, (32, 16)), ("g3", 1, [8, 8, 16, 16], 3, (16, 16))):
+        torch.manual_seed(1234 + in_nc + nb)
+        orig_load, orig_lsd = torch.load, torch.nn.Module.load_state_dict
+        torch.load = lambda *a, **kw: {}
+        torch.nn.Module.load_state_dict = lambda self, sd, strict=True: None
+        try:
+            net = nu.UNet(file_name="", in_nc=in_nc, out_nc=in_nc, nc=nc, nb=nb)
+        finally:
+            torch.load, torch.nn.Module.load_state_dict = orig_load, orig_lsd
+        net.eval()
+        with torch.no_grad():
+            for prm in net.parameters():                      # default init is tiny through 20 layers: scale up so every layer matters
+                prm.mul_(1.5)
+            x = torch.rand((2, in_nc) + hw)
+            y = net(x)
+        for k, v in net.state_dict().items():
+            out[f"{tag}/sd/{k}"] = v.numpy()
+        out[f"{tag}/x"], out[f"{tag}/y"] = x.numpy(), y.numpy()
+        out[f"{tag}/cfg"] = np.array([in_nc, nb] + nc)
+        print(f"  unet {tag}: params {sum(p.numel() for p in net.parameters())}, |y - x| max {float((y - x).abs().max()):.3e}")
+    save("unet.npz", **out)
+
+
 def gen_textfile():
     """SUMMARY text-file strings from the reference's own writer (utils/utils_textfile.py) for a fixed `datas` dict."""
     import importlib.util
@@ -359,6 +389,8 @@ def main():
         gen_loops(ref, TV_CASES, "tv.npz", snapshots=(1, 2, 10))
     if a.long or "long" in todo:
         gen_loops(ref, LONG_CASES, "long.npz", snapshots=())
+    if "unet" in todo:
+        gen_unet(ref)
     if "unstable" in todo:
         gen_loops(ref, UNSTABLE_CASES, "unstable.npz", snapshots=(1, 2, 10))
     if "base" in todo:                                               # ~1 h on 8 vCPUs

@@ -205,3 +205,22 @@ def test_chain_kernel_partial_last_chunk_and_back_to_back_calls():
         for _ in range(20):
             out = e.dncnn_forward(xd)
         assert np.array_equal(out.cpu().numpy(), ref)
+
+
+@pytest.mark.parametrize("shape,variant,name", [((2, 1, 40, 256), 64, "roll_d"), ((1, 1, 24, 256), 64 | 256, "roll_hbm"), ((3, 1, 50, 37), 128 | 512, "tc2"),
+                                                ((3, 1, 50, 37), 128, "chain"), ((1, 3, 64, 64), 128, "chain_colour")])
+def test_body_kernels_are_deterministic_run_to_run(shape, variant, name):
+    """Race canary (compute-sanitizer is closed on the GPU pool, profiles/r02_sanitizer.txt): 12 forward passes of the same input
+    through each body-kernel family give bit-identical outputs."""
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    B, C, H, W = shape
+    w = load_weights(weights_path(SIMPLE[1] if C == 3 else SIMPLE[0]))
+    x = np.random.default_rng(41).random(shape).astype(np.float32)
+    with Engine(B, C, H, W, conv_engine="tcgen05") as e:
+        e.load_dncnn(w)
+        e.set_tc_variant(variant)
+        xd = e.to_device(x)
+        first = e.dncnn_forward(xd).clone()
+        for _ in range(11):
+            assert bool((e.dncnn_forward(xd) == first).all()), name
