@@ -230,7 +230,7 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and its cost model
     // (roll_band_rows) beats the tiles; else the 2-CTA tile kernel (measured faster than the 1-CTA one at every size: half
     // the weight prologue per SM, fewer operand bytes; cfg1 264 vs 285 us per iteration, cfg2 694 vs 792).  The 1-CTA tile
-    // kernel stays as a cross-check.  PDS_TC_VARIANT bit 7 disables row streaming, bit 6 forces it wherever the width
+    // kernel stays as a cross-check.  tc_variant (pds_debug_set_tc_variant) bit 7 disables row streaming, bit 6 forces it wherever the width
     // allows, bit 4 / bit 5 force the 1-CTA / 2-CTA tile kernel, bit 8 makes the row-streaming kernel read e4m3(a) from
     // HBM instead of rebuilding it on chip (then every layer stores it).
     const BodyDispatch bd = body_dispatch(h, nimg);

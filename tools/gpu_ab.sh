@@ -1,9 +1,9 @@
 #!/bin/bash
-# Steady-state A/B of PDS_TC_VARIANT values on the default workload (cfg4, 64 images): gpu_ab.sh V1 V2 ...
+# Steady-state A/B of --tc-variant values (pds_debug_set_tc_variant) on the default workload (cfg4, 64 images): gpu_ab.sh V1 V2 ...
 set -u
 mkdir -p gpurun_out
 for v in "$@"; do
-  PDS_TC_VARIANT=$v timeout 600 python bench.py --steps 6 --warmup 3 --e2e-iters 1 --no-cpu-baseline --no-hbm-probe > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err
+  timeout 600 python bench.py --steps 6 --warmup 3 --e2e-iters 1 --no-cpu-baseline --no-hbm-probe --tc-variant $v > gpurun_out/ab_v$v.json 2> gpurun_out/ab_v$v.err
   python - $v <<'PY'
 import json,sys
 v=sys.argv[1]

@@ -1,9 +1,9 @@
 #!/bin/bash
-# Perf experiments on the body-layer kernel: PDS_TC_VARIANT values given as arguments, cfg4 shape, 16 images.
+# Perf experiments on the body-layer kernel: --tc-variant values (pds_debug_set_tc_variant) given as arguments, cfg4 shape, 16 images.
 set -u
 mkdir -p gpurun_out
 for v in "$@"; do
-  PDS_TC_VARIANT=$v timeout 600 python bench.py --steps 3 --warmup 3 --workload cfg4 --batch 16 --e2e-iters 1 --no-cpu-baseline --no-hbm-probe > gpurun_out/exp_v$v.json 2> gpurun_out/exp_v$v.err
+  timeout 600 python bench.py --steps 3 --warmup 3 --workload cfg4 --batch 16 --e2e-iters 1 --no-cpu-baseline --no-hbm-probe --tc-variant $v > gpurun_out/exp_v$v.json 2> gpurun_out/exp_v$v.err
   python - $v <<'PY'
 import json,sys
 v=sys.argv[1]

@@ -17,9 +17,30 @@ KEEP = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes.sum.per_second", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
         "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
-        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum"]
+
+
+ROLL_ROLES = ""     # filled in below from the current sources (line ranges of the role branches)
+CHAIN_ROLES = ""
+
+
+def role_spec(path, markers, after=0):
+    """name:first-last,... from marker comments in a kernel source: a role starts at its marker line and ends before the next one."""
+    lines = open(path).read().splitlines()
+    pos = []
+    for name, needle in markers:
+        hit = [i + 1 for i, l in enumerate(lines) if needle in l and i + 1 > after]
+        if hit:
+            pos.append((hit[0], name))
+    pos.sort()
+    out = []
+    for k, (ln, name) in enumerate(pos):
+        end = pos[k + 1][0] - 1 if k + 1 < len(pos) else len(lines)
+        out.append(f"{name}:{ln}-{end}")
+    return ",".join(out)
 
 
 def raw_page(rep):
@@ -56,9 +77,23 @@ def summarize(rep, tag, out_name):
 
 
 def main():
-    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    global ROLL_ROLES, CHAIN_ROLES
+    csrc = os.path.join(ROOT, "pnp-pds_b200", "csrc")
+    CHAIN_ROLES = role_spec(os.path.join(csrc, "dncnn_chain.cu"),
+                            [("setup", "extern __shared__ uint8_t smem_raw[];"), ("producer", "// ------------------------------------------------------------ producer"),
+                             ("mma_issuer", "// ------------------------------------------------------------ MMA issuer"),
+                             ("weight_forwarder", "// ------------------------------------------------------------ CTA 1: tell"),
+                             ("publisher", "// ------------------------------------------------------------ publisher"),
+                             ("epilogue", "// ------------------------------------------------------------ epilogue"), ("teardown", "  tc_fence_before();\n  __syncthreads();\n  cluster_sync_all();")])
+    roll = os.path.join(csrc, "dncnn_roll.cu")
+    start = [i + 1 for i, l in enumerate(open(roll).read().splitlines()) if "conv_roll_d_kernel(const" in l]
+    ROLL_ROLES = role_spec(roll, [("setup", "conv_roll_d_kernel("), ("producer", "// ------------------------------------------------------------ TMA producer"),
+                                  ("mma_issuer", "// ------------------------------------------------------------ MMA issuer"),
+                                  ("epilogue", "// ------------------------------------------------------------ epilogue"),
+                                  ("converters", "// ------------------------------------------------------------ converters")], after=(start[0] - 1 if start else 276))
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
     os.makedirs(OUT, exist_ok=True)
-    for name in ("default", "cfg1", "cfg2", "cfg3", "cfg2b", "cfg5"):
+    for name in ("default", "cfg1", "cfg1_per_layer", "cfg2", "cfg3", "cfg2b", "cfg5"):
         p = os.path.join(SRC, f"BENCH_{name}.json")
         if os.path.exists(p):
             shutil.copy(p, os.path.join(OUT, f"{tag}_bench_{name}.json"))
@@ -100,6 +135,26 @@ def main():
     rep = os.path.join(SRC, "prof_pointwise.ncu-rep")
     if os.path.exists(rep):
         summarize(rep, tag, "ncu_pointwise.json")
+    for name, outn in (("prof_chain", "ncu_chain.json"), ("prof_blur", "ncu_blur.json")):
+        rep = os.path.join(SRC, name + ".ncu-rep")
+        if os.path.exists(rep):
+            summarize(rep, tag, outn)
+    if os.path.exists(os.path.join(SRC, "launches_cfg1.csv")):
+        shutil.copy(os.path.join(SRC, "launches_cfg1.csv"), os.path.join(OUT, f"{tag}_launches_cfg1.csv"))
+    for name in ("timeline_256.txt",):
+        if os.path.exists(os.path.join(SRC, name)):
+            shutil.copy(os.path.join(SRC, name), os.path.join(OUT, f"{tag}_chain_{name}"))
+    # warp-stall samples by warp role (source-line ranges of the kernels' role branches)
+    roles = {"prof_conv_layers": ("dncnn_roll.cu", ROLL_ROLES, "conv_roll_d_kernel", "ncu_roll_roles.json"),
+             "prof_chain": ("dncnn_chain.cu", CHAIN_ROLES, "conv_chain_kernel", "ncu_chain_roles.json")}
+    for name, (src, spec, kern, outn) in roles.items():
+        rep = os.path.join(SRC, name + ".ncu-rep")
+        if os.path.exists(rep) and spec:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_roles.py"), rep, src, spec, kern], capture_output=True, text=True)
+            if r.returncode == 0 and r.stdout.strip():
+                open(os.path.join(OUT, f"{tag}_{outn}"), "w").write(r.stdout)
+            else:
+                print("ncu_roles failed for", name, r.stderr[-400:])
     print(sorted(os.listdir(OUT)))
 
 
