@@ -199,7 +199,8 @@ int pds_debug_set_conv_engine(pds_handle_t h, int engine);
  * bit 6 forces the row-streaming body kernels (dncnn_roll.cu) wherever the image is at least 128 pixels wide, bit 7 disables
  * them, bit 8 makes them read the e4m3(a) operand from HBM instead of rebuilding it on chip (every layer then stores it),
  * bit 9 disables the chain kernel (all body layers of a small launch in one persistent launch) in favour of one tile-kernel
- * launch per layer */
+ * launch per layer, bits 11 / 12 are timing probes of the chain kernel's MMA issue order (12 gives wrong results by design),
+ * bit 13 makes the blur stencils ignore the compile-time tap list of blur_models/blur_1.mat (generic kernels: the cross-check) */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant);
 /* SM-cycle-counter stamps of the chain kernel's pipeline events (dncnn_chain.cu: flags polled, TMA issued, TMEM stage free, first
  * plane landed, MMAs issued, accumulator ready, stored, published) for the first 64 units of CTA 0 of the first 4 clusters:

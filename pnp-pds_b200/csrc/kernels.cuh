@@ -66,6 +66,7 @@ struct BlurTaps {            // device arrays, built by pds_set_blur_kernel
   const short2* off[2];      // (dy, dx) per tap: out[i,j] += w * in[i+dy, j+dx] (periodic)
   int ntaps;
   int ry, rx;                // max |dy|, max |dx|
+  int debug_generic;         // test hook: 1 = never use the compile-time tap list of blur_1.mat (the generic kernels are the cross-check)
   const float* w_host;       // host copies (owned by the handle): the register-tiled stencil takes the weight box by value
   const short2* off_host[2];
 };

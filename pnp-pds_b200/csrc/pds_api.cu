@@ -1117,6 +1117,7 @@ int pds_debug_body_kernel(pds_handle_t h, int nimg) {
 int pds_debug_set_tc_variant(pds_handle_t h, int variant) {
   if (!h) return 1;
   h->tc_variant = variant;
+  h->taps.debug_generic = (variant & 8192) ? 1 : 0;     // bit 13: generic blur stencils instead of blur_1.mat's compile-time tap list
   return 0;
 }
 

@@ -141,7 +141,15 @@ __global__ void __launch_bounds__(kThreads) blur_kernel(BlurArgs a) {
 // branch on that constant.  24 FMAs per shared-memory load instruction: the stencil runs on the FP32 pipe, not on the LSU.
 // OX = outputs per thread along x: 16 for launches that fill the GPU (128 x 32 tiles), 4 for small ones (32 x 32 tiles: a single
 // 256 x 256 image is 64 blocks instead of 16, and a thread's serial work — what bounds a launch that small — is a quarter).
-template <int MODE, int METHOD, int RY, int RX, int OX>
+// SPEC: 0 = any kernel (zero taps skipped by a uniform branch on the constant-bank weight); 1 / 2 = the non-zero pattern of
+// blur_models/blur_1.mat — the one kernel the reference's driver ever selects (main.py:27) — in the Phi / Phi^T orientation, known at
+// compile time: exactly its 109 x OX FMAs per thread, weights still read from the constant bank, no test, no branch, no weight
+// register (the generic form spends 30 % of its instructions on LDC / FSETP / BRA around the 153 candidate taps).
+__device__ constexpr unsigned kBlur1Rows[2][17] = {
+    {480, 480, 496, 504, 508, 510, 254, 255, 255, 255, 255, 255, 127, 127, 63, 31, 14},     // Phi:   bit dx of box row dy
+    {224, 496, 504, 508, 508, 510, 510, 510, 510, 510, 254, 255, 127, 63, 31, 15, 15}};     // Phi^T
+
+template <int MODE, int METHOD, int RY, int RX, int OX, int SPEC = 0>
 __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__ BlurArgs a) {
   constexpr int TWR = 8 * OX, THR = 32;
   constexpr int HC = TWR + 2 * RX, HR = THR + 2 * RY;
@@ -195,7 +203,12 @@ __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__
 #pragma unroll
     for (int dxi = 0; dxi < 2 * RX + 1; ++dxi) {
       const float w = a.wbox[dyi * (2 * RX + 1) + dxi];      // constant-bank operand
-      if (w != 0.f) {                       // uniform: the weight does not depend on the thread
+      if constexpr (SPEC != 0) {
+        if ((kBlur1Rows[SPEC - 1][dyi] >> dxi) & 1u) {       // compile-time after unrolling
+#pragma unroll
+          for (int c = 0; c < OX; ++c) acc[c] = fmaf(w, v[c + dxi], acc[c]);
+        }
+      } else if (w != 0.f) {                // uniform: the weight does not depend on the thread
 #pragma unroll
         for (int c = 0; c < OX; ++c) acc[c] = fmaf(w, v[c + dxi], acc[c]);
       }
@@ -296,7 +309,7 @@ constexpr size_t rt_smem_bytes() {
   return (size_t)(HR * PITCH) * sizeof(float);
 }
 
-template <int MODE, int METHOD, int RY, int RX, int OX>
+template <int MODE, int METHOD, int RY, int RX, int OX, int SPEC = 0>
 cudaError_t launch_rt_ox(const BlurArgs& a0, const Dims& d, cudaStream_t st) {
   BlurArgs a = a0;
   a.tiles_x = (d.W + 8 * OX - 1) / (8 * OX);
@@ -304,13 +317,17 @@ cudaError_t launch_rt_ox(const BlurArgs& a0, const Dims& d, cudaStream_t st) {
   dim3 grid(a.tiles_x * tiles_y, d.B * d.C);
   static PerDeviceOnce once;
   if (once.first_use()) {
-    cudaError_t e = cudaFuncSetAttribute(blur_rt_kernel<MODE, METHOD, RY, RX, OX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(blur_rt_kernel<MODE, METHOD, RY, RX, OX, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)rt_smem_bytes<RY, RX, OX>());
     if (e != cudaSuccess) { once.retract(); return e; }
   }
-  blur_rt_kernel<MODE, METHOD, RY, RX, OX><<<grid, 256, rt_smem_bytes<RY, RX, OX>(), st>>>(a);
+  blur_rt_kernel<MODE, METHOD, RY, RX, OX, SPEC><<<grid, 256, rt_smem_bytes<RY, RX, OX>(), st>>>(a);
   return cudaGetLastError();
 }
+
+constexpr unsigned kBlur1RowsHost[2][17] = {
+    {480, 480, 496, 504, 508, 510, 254, 255, 255, 255, 255, 255, 127, 127, 63, 31, 14},
+    {224, 496, 504, 508, 508, 510, 510, 510, 510, 510, 254, 255, 127, 63, 31, 15, 15}};
 
 inline int blur_num_sms() {
   static int n = 0;
@@ -335,7 +352,21 @@ cudaError_t launch_rt(BlurArgs& a, const Dims& d, const BlurTaps& t, int which, 
     a.wbox[((int)t.off_host[which][k].x + RY) * (2 * RX + 1) + (int)t.off_host[which][k].y + RX] = t.w_host[k];
   // 128 x 32 tiles when they give every SM two blocks, 32 x 32 tiles otherwise
   const long long blocks16 = (long long)((d.W + 127) / 128) * ((d.H + 31) / 32) * d.B * d.C;
-  if (blocks16 >= 2LL * blur_num_sms()) return launch_rt_ox<MODE, METHOD, RY, RX, 16>(a, d, st);
+  const bool big = blocks16 >= 2LL * blur_num_sms();
+  if constexpr (RY == 8 && RX == 4) {
+    // blur_1.mat's own non-zero pattern (in this direction's orientation): the compile-time tap list
+    bool match = !(t.debug_generic);
+    for (int r = 0; r < 17 && match; ++r) {
+      unsigned bits = 0;
+      for (int c = 0; c < 9; ++c) bits |= (a.wbox[r * 9 + c] != 0.f ? 1u : 0u) << c;
+      match = bits == kBlur1RowsHost[which][r];
+    }
+    if (match) {
+      if (which == 0) return big ? launch_rt_ox<MODE, METHOD, RY, RX, 16, 1>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 4, 1>(a, d, st);
+      return big ? launch_rt_ox<MODE, METHOD, RY, RX, 16, 2>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 4, 2>(a, d, st);
+    }
+  }
+  if (big) return launch_rt_ox<MODE, METHOD, RY, RX, 16>(a, d, st);
   return launch_rt_ox<MODE, METHOD, RY, RX, 4>(a, d, st);
 }
 

@@ -124,3 +124,30 @@ def test_prox_gkl(ops, g_ops):
     ref = O.prox_gkl(x, 0.01, 100.0, x0)
     got = ops.prox_GKL(x, 0.01, 100.0, x0)
     assert np.max(np.abs(got - ref) / ref) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 64, 64), (1, 3, 96, 200), (40, 1, 128, 256)])
+def test_blur1_compile_time_tap_list_matches_generic_stencil(assets, shape):
+    """blur_models/blur_1.mat has its own stencil instantiation (non-zero pattern known at compile time, pds_blur.cu SPEC = 1 / 2);
+    same taps in the same order as the generic kernels (tc_variant bit 13) -> bit-identical Phi, Phi^T and loop iterates, for the
+    32 x 32 and the 128 x 32 tile variants.  A kernel with a different pattern (one tap removed) takes the generic path."""
+    from pnp_pds_b200.engine import Engine
+    B, C, H, W = shape
+    x = np.random.default_rng(5).random(shape).astype(np.float32)
+    outs = {}
+    for name, variant in (("spec", 0), ("generic", 8192)):
+        with Engine(B, C, H, W, method="A", deg_op="blur", max_iter=4) as e:
+            e.set_blur_kernel(assets["blur_1"])
+            e.set_tc_variant(variant)
+            xd = e.to_device(x)
+            outs[name] = (e.phi(xd).cpu().numpy(), e.phi_adj(xd).cpu().numpy())
+    assert np.array_equal(outs["spec"][0], outs["generic"][0]) and np.array_equal(outs["spec"][1], outs["generic"][1])
+    h2 = np.array(assets["blur_1"], dtype=np.float64)
+    a, b = np.argwhere(h2 != 0)[3]
+    h2[a, b] = 0.0
+    with Engine(B, C, H, W, method="A", deg_op="blur", max_iter=4) as e:
+        e.set_blur_kernel(h2)
+        xd = e.to_device(x)
+        y = e.phi(xd).cpu().numpy()
+    ref = np.stack([O.blur_phi(x[i].astype(np.float64), h2) for i in range(min(B, 2))])
+    assert np.max(np.abs(y[: min(B, 2)] - ref.reshape(y[: min(B, 2)].shape))) < 2e-6

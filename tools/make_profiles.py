@@ -150,7 +150,8 @@ def main():
     for name, (src, spec, kern, outn) in roles.items():
         rep = os.path.join(SRC, name + ".ncu-rep")
         if os.path.exists(rep) and spec:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_roles.py"), rep, src, spec, kern], capture_output=True, text=True)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_roles.py"), rep, os.path.join(ROOT, "pnp-pds_b200", "csrc", src), spec, kern],
+                               capture_output=True, text=True)
             if r.returncode == 0 and r.stdout.strip():
                 open(os.path.join(OUT, f"{tag}_{outn}"), "w").write(r.stdout)
             else:
