@@ -434,6 +434,241 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 }  // namespace first
 
 // ---------------------------------------------------------------------------------------------
+// First layer, tap-shifted form (the default; conv_first_tc_kernel above is kept as the cross-check, tc_variant bit 15).
+// The im2col kernel above spends half of its issue slots building the 128 x 27 patch matrix (ncu: producers 47 % of the
+// stall samples, epilogue 48 %).  Here nothing is gathered: every halo pixel of the 18 x 10 window is ONE 32-byte record of 16
+// fp16 K-slots
+//     [ a_hi(c) | a_lo(c) | a_hi(c) | 1 1 1 | 0 .. ]        c = 0..Cin-1,  a = a_hi + a_lo
+// stored as two un-swizzled K-major planes (slots 0-7 / 8-15, 16 bytes per pixel each), and tap (dy,dx) is the same window read
+// through a descriptor whose start address is shifted by (dy*10 + dx) * 16 bytes (8-row groups 160 bytes apart = one window
+// row) — the trick of the body layers at K = 16 instead of 64.  The B rows of tap t hold
+//     [ w_hi(c) | w_hi(c) | w_lo(c) | bias as three fp16 terms (centre tap only) | 0 .. ]
+// so one M=128, N=64, K=16 MMA per tap accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ bias): 9 MMAs per tile into ONE fp32
+// accumulator, no correction accumulator, no bias add in the epilogue.  Six producer warps write the 180 records of a tile
+// (one pixel per thread, loads issued three tiles ahead); sixteen epilogue warps in four groups drain four TMEM stages, so the
+// kernel is bound by writing 192 (or 256) bytes per pixel.
+// ---------------------------------------------------------------------------------------------
+namespace first2 {
+constexpr int kStagesA = 4, kAcc = 4;
+constexpr int kProdThreads = 192, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
+constexpr int kWinPix = kHaloRows * kHaloPitch;                     // 180 records per tile
+constexpr uint32_t kChunkPlane = kWinPix * 16;                      // 2880 bytes: K-slots 0-7 (plane 0) / 8-15 (plane 1) of every record
+constexpr uint32_t kStageBytes = 2 * kChunkPlane;
+constexpr uint32_t kWTap = 2 * 64 * 16, kWBytesF2 = 9 * kWTap;      // per tap: [chunk][oc][8 halves]
+constexpr uint32_t kOffA2 = kWBytesF2, kOffBar2 = kOffA2 + kStagesA * kStageBytes;
+constexpr uint32_t kSmemBytesF2 = kOffBar2 + 256 + 128;
+constexpr uint32_t kIdescF2 = kIdescBase | ((64u >> 3) << 17);
+static_assert(kOffA2 % 16 == 0 && kStageBytes % 16 == 0 && kOffBar2 % 8 == 0, "alignment");
+
+// K-major, no swizzle: 8 rows x 16 bytes per core matrix (rows 16 bytes apart), lbo = distance between the two K chunks of an MMA,
+// sbo = distance between 8-row groups
+__device__ __forceinline__ uint64_t desc_k_none(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
+}
+
+// 32 channels [c0, c0+32) of one pixel from ONE accumulator that already holds the bias: LeakyReLU, then the stores of
+// store_half_row (tc_common.cuh): fp16(v) | e4m3(fp16(v)) (if write_a8) | e4m3((v - fp16(v)) 2^10)
+__device__ __forceinline__ void store_half_row1(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d)[32], int c0, float slope, int write_a8) {
+  uint32_t a8[8], l8[8];
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t hi[8];
+    float l[16];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = q * 16 + 2 * k;
+      float v0 = __uint_as_float(d[c]), v1 = __uint_as_float(d[c + 1]);
+      v0 = fmaxf(v0, v0 * slope);
+      v1 = fmaxf(v1, v1 * slope);
+      const __half2 hh = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hh);
+      hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
+      l[2 * k] = (v0 - hf.x) * kActLoScale;
+      l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
+    }
+    st_global_256(dst_p0 + c0 + q * 16, hi);
+    if (write_a8) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) a8[q * 4 + k] = e4m3x2_from_f16x2(hi[2 * k]) | (e4m3x2_from_f16x2(hi[2 * k + 1]) << 16);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
+  }
+  if (write_a8) st_global_256(dst_p1 + c0, a8);
+  st_global_256(dst_p1 + 64 + c0, l8);
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(first::FirstArgs a) {
+  static_assert(3 * CIN + 3 <= 16, "K-slots of one record");
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  const uint32_t sW = base, sA = base + kOffA2, sBar = base + kOffBar2;
+  // barriers: fullA[4] @0, emptyA[4] @32, wfull @64, tfull[4] @72, tempty[4] @104, tmem slot @136
+  const uint32_t bFull = sBar, bEmpty = sBar + 32, bW = sBar + 64, bTFull = sBar + 72, bTEmpty = sBar + 104, sTmemSlot = sBar + 136;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesA; ++i) {
+      mbar_init(bFull + 8 * i, kProdThreads);      // every producer thread arrives after its record is written
+      mbar_init(bEmpty + 8 * i, 1);
+    }
+    mbar_init(bW, 1);
+    for (int i = 0; i < kAcc; ++i) {
+      mbar_init(bTFull + 8 * i, 1);
+      mbar_init(bTEmpty + 8 * i, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_raw + kOffBar2 + 136);
+  const int per_img = a.tiles_x * a.tiles_y;
+  const size_t hw = (size_t)a.H * a.W;
+
+  if (warp < kMmaWarp2) {
+    // ------------------------------------------------------------ record producers: thread p = window pixel p (p < 180)
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bW, kWBytesF2);
+      bulk_load(sW, a.w_img, kWBytesF2, bW);
+    }
+    const int p = threadIdx.x;
+    const bool active = p < kWinPix;
+    const int hy = p / kHaloPitch, hx = p - hy * kHaloPitch;
+    constexpr int kDepth = 3;
+    float pre[kDepth][CIN];
+    bool inside[kDepth];
+    auto fetch = [&](int tile, float (&r)[CIN], bool& in_img) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int gy = (rem / a.tiles_x) * kTileRows - 1 + hy, gx = (rem % a.tiles_x) * kTileCols - 1 + hx;
+      in_img = active && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) r[c] = in_img ? __ldg(a.in + ((size_t)(img * CIN + c) * a.H + gy) * a.W + gx) : 0.f;
+    };
+    const int tstep = (int)gridDim.x;
+#pragma unroll
+    for (int dd = 0; dd < kDepth; ++dd) {
+      inside[dd] = false;
+      const int t0 = blockIdx.x + dd * tstep;
+      if (t0 < a.ntiles) fetch(t0, pre[dd], inside[dd]);
+    }
+    int it = 0;
+    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += kDepth * tstep) {
+#pragma unroll
+      for (int dd = 0; dd < kDepth; ++dd, ++it) {
+        const int tile = tile0 + dd * tstep;
+        if (tile >= a.ntiles) break;
+        // fp16 hi / lo split of the (clamped, denoiser.py:40) input; pixels outside the image are all-zero records = the
+        // convolution's zero padding (their "1" slots only ever meet zero weights: the bias sits in the centre tap)
+        uint32_t rec[8];
+        {
+          __half h16[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) h16[k] = __float2half_rn(0.f);
+          if (inside[dd]) {
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+              const float v = a.clamp_in ? fminf(fmaxf(pre[dd][c], 0.f), 1.f) : pre[dd][c];
+              const __half hi = __float2half_rn(v);
+              const __half lo = __float2half_rn(v - __half2float(hi));
+              h16[c] = hi;
+              h16[CIN + c] = lo;
+              h16[2 * CIN + c] = hi;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) h16[3 * CIN + k] = __float2half_rn(1.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            rec[k] = (uint32_t)__half_as_ushort(h16[2 * k]) | ((uint32_t)__half_as_ushort(h16[2 * k + 1]) << 16);
+        }
+        const uint32_t stage = it % kStagesA, use = it / kStagesA;
+        mbar_wait(bEmpty + 8 * stage, (use & 1) ^ 1);
+        if (active) {
+          const uint32_t dst = sA + stage * kStageBytes + (uint32_t)p * 16u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(rec[0]), "r"(rec[1]), "r"(rec[2]), "r"(rec[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kChunkPlane), "r"(rec[4]), "r"(rec[5]), "r"(rec[6]), "r"(rec[7]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        mbar_arrive(bFull + 8 * stage);
+        // prefetch for the tile kDepth rounds ahead — after the releasing arrive, whose MEMBAR would otherwise wait for these loads
+        inside[dd] = false;
+        if (tile + kDepth * tstep < a.ntiles) fetch(tile + kDepth * tstep, pre[dd], inside[dd]);
+      }
+    }
+  } else if (warp == kMmaWarp2) {
+    // ------------------------------------------------------------ MMA issuer: nine K=16 MMAs per tile, one per tap
+    mbar_wait(bW, 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it % kAcc, stage = it % kStagesA, use = it / kStagesA;
+      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it / kAcc) & 1) ^ 1));
+      mbar_wait(bFull + 8 * stage, use & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * 64u;
+      const uint32_t a0 = sA + stage * kStageBytes;
+      if (elect_one()) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t shift = (uint32_t)((t / 3) * kHaloPitch + (t % 3)) * 16u;
+          umma_f16(d_tmem, desc_k_none(a0 + shift, kChunkPlane, kHaloPitch * 16), desc_k_none(sW + t * kWTap, 64 * 16, 128), kIdescF2,
+                   t ? 1u : 0u);
+        }
+        umma_commit(bEmpty + 8 * stage);
+        umma_commit(bTFull + 8 * acc);
+      }
+      __syncwarp();
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------------------------------------ epilogue: four groups of four warps, group g drains the tiles
+    // with it % 4 == g = accumulator stage g
+    const int q = warp & 3;                               // TMEM lane quadrant this warp may read
+    const int grp = (warp - kEpiWarp0) >> 2;
+    const int m = q * 32 + lane;
+    const int ty = m >> 3, tx = m & 7;
+    int it = grp;
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += kAcc * gridDim.x, it += kAcc) {
+      const int img = tile / per_img, rem = tile - img * per_img;
+      const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
+      const uint32_t acc = (uint32_t)grp;
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it / kAcc) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u;
+      const bool st = y < a.H && x < a.W;
+      const size_t pix = (size_t)y * a.W + x;
+      __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
+      uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+      {
+        uint32_t r0[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld_wait();
+        if (st) store_half_row1(o_p0, o_p1, r0, 0, a.slope, a.write_a8);
+      }
+      {
+        uint32_t r1[32];
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
+        if (st) store_half_row1(o_p0, o_p1, r1, 32, a.slope, a.write_a8);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+}  // namespace first2
+
+// ---------------------------------------------------------------------------------------------
 // Last layer (64 -> Cout = 1|3).  With N this small, one MMA group per tap is bound by re-reading the same A tile from
 // shared memory nine times.  Instead the contraction over the 64 input channels is done ONCE per halo pixel for all
 // nine taps at the same time:
@@ -445,6 +680,7 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 // ---------------------------------------------------------------------------------------------
 namespace last {
 constexpr int kSlotsL = 6;
+constexpr int kThreadsL = 64 + 2 * 128;                   // TMA warp, MMA warp, two epilogue groups of four warps
 constexpr int kNL = 32;                                   // B rows (tap*C + c), zero beyond 9*C
 constexpr uint32_t kWTileL = kNL * 128, kWBytesL = 2 * kWTileL;   // fp16 tile + e4m3 tile
 constexpr int kHaloPix = kHaloRows * kHaloPitch;          // 180
@@ -456,7 +692,7 @@ constexpr uint32_t kSmemBytesL = kOffPL + 2 * kHaloPix * kPStride * 4 + 1024;
 constexpr uint32_t kIdescL = kIdescBase | ((uint32_t)(kNL >> 3) << 17);
 
 template <int C>
-__global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+__global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -550,16 +786,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue: TMEM -> P (shared) -> 3x3 gather -> planar fp32
+    // ------------------------------------------------------------ epilogue: TMEM -> P (shared) -> 3x3 gather -> planar fp32.
+    // Two groups of four warps: a tile's epilogue is one dependent chain per thread (TMEM read, P write, barrier, gather, store)
+    // and this layer has only 16 MMAs per tile to hide it behind; group g drains the tiles with it % 2 == g, i.e. accumulator
+    // stage g, through its own P buffer and named barrier.
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int t = q * 32 + lane;
     const int ty = t >> 3, tx = t & 7;
     const size_t hw = (size_t)a.H * a.W;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+    int it = grp;
+    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, it += 2) {
       const int img = tile / per_img, rem = tile - img * per_img;
       const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
-      const uint32_t acc = it & 1;
+      const uint32_t acc = (uint32_t)grp;
       // residual input of this thread's pixel: issued before the wait so its latency hides behind the MMAs
       const bool live = y < a.H && x < a.W;
       const size_t pix = (size_t)y * a.W + x;
@@ -569,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
-      float* Pb = P + (it & 1) * (kHaloPix * kPStride);
+      float* Pb = P + grp * (kHaloPix * kPStride);
       {
         uint32_t r0[32], r1[32], r2[32], r3[32];
         tmem_ld32(taddr, r0);
@@ -580,6 +820,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
+        // the group's previous tile has been gathered out of Pb by all four warps
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         float* row0 = Pb + t * kPStride;                   // halo pixel t            (block 0)
 #pragma unroll
         for (int n = 0; n < 9 * C; ++n) row0[n] = fmaf(__uint_as_float(r2[n]), a.lo_scale, __uint_as_float(r0[n]));
@@ -589,7 +832,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_last_tc_kernel(const __grid_
           for (int n = 0; n < 9 * C; ++n) row1[n] = fmaf(__uint_as_float(r3[n]), a.lo_scale, __uint_as_float(r1[n]));
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");       // P of this tile complete; also fences the buffer reused two tiles later
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // P of this tile complete
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
       if (live) {
         // out = clamp(sign * (conv + bias) + clamp(net_in))   (basic_models.py:36, denoiser.py:40-42, network_dncnn.py:77)
         float sum[C];
@@ -932,6 +1176,10 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
       e = cudaFuncSetAttribute(first::conv_first_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first::kSmemBytesF);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(first::conv_first_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first::kSmemBytesF);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(first2::conv_first2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first2::kSmemBytesF2);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(first2::conv_first2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)first2::kSmemBytesF2);
     if (e != cudaSuccess) {
       set_error(std::string("cudaFuncSetAttribute(conv_tc_kernel): ") + cudaGetErrorString(e));
       rc = 1;
@@ -992,10 +1240,10 @@ cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnL
 }
 
 cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
-                                 int write_a8, cudaStream_t st) {
+                                 int write_a8, int im2col, cudaStream_t st) {
   first::FirstArgs a{};
   a.in = in;
-  a.w_img = L.w_first_tc;
+  a.w_img = im2col ? L.w_first_tc : L.w_first_tc2;
   a.bias = L.bias;
   a.out = plan->act[0];
   a.slope = slope;
@@ -1008,6 +1256,12 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
   a.tiles_y = (plan->H + kTileRows - 1) / kTileRows;
   a.ntiles = a.tiles_x * a.tiles_y * nimg;
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
+  if (!im2col) {
+    if (C == 1) first2::conv_first2_kernel<1><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(a);
+    else if (C == 3) first2::conv_first2_kernel<3><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(a);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+  }
   if (C == 1) first::conv_first_tc_kernel<1><<<grid, first::kThreadsF, first::kSmemBytesF, st>>>(a);
   else if (C == 3) first::conv_first_tc_kernel<3><<<grid, first::kThreadsF, first::kSmemBytesF, st>>>(a);
   else return cudaErrorInvalidValue;
@@ -1027,8 +1281,8 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
   a.lo_scale = L.lo_scale;
   fill_common(a, plan, nimg);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  if (C == 1) return launch_pdl(last::conv_last_tc_kernel<1>, grid, kThreads, last::kSmemBytesL, st, plan->map[in_buf], a);
-  if (C == 3) return launch_pdl(last::conv_last_tc_kernel<3>, grid, kThreads, last::kSmemBytesL, st, plan->map[in_buf], a);
+  if (C == 1) return launch_pdl(last::conv_last_tc_kernel<1>, grid, last::kThreadsL, last::kSmemBytesL, st, plan->map[in_buf], a);
+  if (C == 3) return launch_pdl(last::conv_last_tc_kernel<3>, grid, last::kThreadsL, last::kSmemBytesL, st, plan->map[in_buf], a);
   return cudaErrorInvalidValue;
 }
 

@@ -67,6 +67,7 @@ struct BlurTaps {            // device arrays, built by pds_set_blur_kernel
   int ntaps;
   int ry, rx;                // max |dy|, max |dx|
   int debug_generic;         // test hook: 1 = never use the compile-time tap list of blur_1.mat (the generic kernels are the cross-check)
+  int debug_ox;              // test hook: outputs per thread of the register-tiled stencil for large launches (0 = default)
   const float* w_host;       // host copies (owned by the handle): the register-tiled stencil takes the weight box by value
   const short2* off_host[2];
 };
@@ -96,6 +97,8 @@ struct DncnnLayerW {
   const float* w_first_host;  // HOST [9*Cin][64] (k = tap*Cin + ci): handed to the first-layer kernel by value (constant bank)
   const float* bias_host;     // HOST [64] bias of the first layer
   const __half* w_first_tc;   // tcgen05 first layer: [w_hi 64 rows ; w_lo 64 rows] x 128 B, k = tap*Cin+ci in the first 27 halves, swizzled
+  const __half* w_first_tc2;  // tap-shifted first layer (dncnn_tc.cu first2): [tap 9][K chunk 2][oc 64][8 halves], K-slots
+                              // [w_hi(c) | w_hi(c) | w_lo(c) | bias in three fp16 terms (centre tap) | 0]
   const float* w_mid;     // [64 ci][9][64 oc] fp32                      SIMT engine
   const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][fp16 tile | e4m3 tile][64 oc][128 B], 128B-swizzled rows
   const __half* w_mid_tc2; // 2-CTA engine: [cta 2][tap 9][fp16 tile 32 rows | e4m3 tile 32 rows][128 B], swizzled
@@ -118,8 +121,9 @@ void tc_plan_destroy(TcPlan* p);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 // write_a8: also store the e4m3(fp16(v)) half of plane 1 (0 when the next layer is the row-streaming kernel, which rebuilds it)
+// im2col: 1 = the im2col kernel (cross-check), 0 = the tap-shifted kernel (default)
 cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in, const DncnnLayerW& L, float slope, int clamp_in,
-                                 int write_a8, cudaStream_t st);
+                                 int write_a8, int im2col, cudaStream_t st);
 cudaError_t launch_conv_mid_tc2(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const DncnnLayerW& L, const float* net_in,
                                 float residual_sign, int clamp, float* out, cudaStream_t st);

@@ -238,7 +238,7 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const bool two_cta = bd.two_cta;
     const bool derive = band > 0 && !(h->tc_variant & 256);
     if (h->conv_engine == PDS_CONV_TCGEN05) {
-      PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, derive ? 0 : 1, st));
+      PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, derive ? 0 : 1, (h->tc_variant & 32768) ? 1 : 0, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));
     }
@@ -801,6 +801,32 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
         PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
         L.w_first_tc = dh;
       }
+      {
+        // tap-shifted first layer (dncnn_tc.cu first2): [tap][K chunk][oc][8 halves]; K-slot s of a B row:
+        //   [0,ci) w_hi, [ci,2ci) w_hi, [2ci,3ci) w_lo, 3ci..3ci+2 = the bias as three fp16 terms (centre tap only), rest 0
+        std::vector<__half> img((size_t)9 * 2 * 64 * 8, __float2half_rn(0.f));
+        auto put = [&](int tp, int o, int s, float v) { img[(((size_t)tp * 2 + (s >> 3)) * 64 + o) * 8 + (s & 7)] = __float2half_rn(v); };
+        for (int o = 0; o < co; ++o) {
+          for (int c = 0; c < ci; ++c)
+            for (int tp = 0; tp < 9; ++tp) {
+              const float v = w[((size_t)o * ci + c) * 9 + tp];
+              const float hi = __half2float(__float2half_rn(v));
+              put(tp, o, c, hi);
+              put(tp, o, ci + c, hi);
+              put(tp, o, 2 * ci + c, v - hi);
+            }
+          float rem = b[o];
+          for (int k = 0; k < 3; ++k) {
+            const float t = __half2float(__float2half_rn(rem));
+            put(4, o, 3 * ci + k, t);
+            rem -= t;
+          }
+        }
+        __half* dh = nullptr;
+        PDS_TRY(dev_alloc(h, &dh, img.size()));
+        PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));
+        L.w_first_tc2 = dh;
+      }
       h->first_w_host = buf;
       h->first_b_host.assign(b, b + co);
       L.w_first_host = h->first_w_host.data();
@@ -1117,7 +1143,8 @@ int pds_debug_body_kernel(pds_handle_t h, int nimg) {
 int pds_debug_set_tc_variant(pds_handle_t h, int variant) {
   if (!h) return 1;
   h->tc_variant = variant;
-  h->taps.debug_generic = (variant & 8192) ? 1 : 0;     // bit 13: generic blur stencils instead of blur_1.mat's compile-time tap list
+  h->taps.debug_generic = (variant & 8192) ? 1 : 0;
+  h->taps.debug_ox = (variant & 16384) ? 8 : 0;          // bit 14: 64 x 32 stencil tiles (8 outputs per thread) for large launches     // bit 13: generic blur stencils instead of blur_1.mat's compile-time tap list
   return 0;
 }
 

@@ -150,7 +150,7 @@ __device__ constexpr unsigned kBlur1Rows[2][17] = {
     {224, 496, 504, 508, 508, 510, 510, 510, 510, 510, 254, 255, 127, 63, 31, 15, 15}};     // Phi^T
 
 template <int MODE, int METHOD, int RY, int RX, int OX, int SPEC = 0>
-__global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__ BlurArgs a) {
+__global__ void __launch_bounds__(256, OX == 8 ? (MODE == kDual ? 4 : 5) : 3) blur_rt_kernel(const __grid_constant__ BlurArgs a) {
   constexpr int TWR = 8 * OX, THR = 32;
   constexpr int HC = TWR + 2 * RX, HR = THR + 2 * RY;
   constexpr int PITCH = ((HC + 27) / 32) * 32 + 4;
@@ -159,16 +159,113 @@ __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__
   extern __shared__ __align__(16) float smem[];
   float* tile = smem;                       // [HR][PITCH]
   __shared__ double red[NACC * 8];
+  __shared__ float sg_s;
   const Dims d = a.s.d;
   const int plane = blockIdx.y;
   const int b = plane / d.C;
+  // sigma of the lazy l2-ball form: one double sqrt per block (published by the barrier that ends the staging phase)
+  if constexpr (MODE != kApply) {
+    if (threadIdx.x == 0) sg_s = item_sigma(METHOD, a.s.sums_prev, b, a.s.prm[b]);
+  }
   const int tyi = blockIdx.x / a.tiles_x, txi = blockIdx.x % a.tiles_x;
   const int x0 = txi * TWR, y0 = tyi * THR;
   const size_t pbase = (size_t)plane * d.hw;
 
+  // The thread's own outputs: OX consecutive columns of row y0 + lane.  The operands of the pointwise tail (x for the primal
+  // step; x+, x, t, b [, s+, s] [, x_true] for the dual step) are DRAM reads the tail would wait for in full: all loads of a group
+  // of GQ float4s are issued before the first is used, and when the whole thread is one group that fits the register budget
+  // (primal: one operand; dual on the small 32 x 32 tiles: five) they are issued HERE, before the staging phase, so their
+  // latency is paid together with the halo loads'.  Otherwise the dual tail works on four outputs at a time.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gy = y0 + lane, gx0 = x0 + OX * warp;
+  const bool live = gy < d.H && gx0 < d.W;
+  const size_t g0 = pbase + (size_t)gy * d.W + gx0;
+  const bool vec = ((d.W & 3) == 0);       // rows start 16-byte aligned and a float4 is never split by the edge
+  const int nvalid = (d.W - gx0) < OX ? (d.W - gx0) : OX;
+  auto load4 = [&](const float* base, int q, float (&r)[4]) {
+    if (vec) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(base + g0) + q);
+      r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) r[c] = (4 * q + c < nvalid) ? __ldg(base + g0 + 4 * q + c) : 0.f;
+    }
+  };
+  auto store4 = [&](float* base, int q, const float (&r)[4]) {
+    if (vec) {
+      *(reinterpret_cast<float4*>(base + g0) + q) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (4 * q + c < nvalid) base[g0 + 4 * q + c] = r[c];
+    }
+  };
+  constexpr bool kEarly = MODE == kPrimal || (MODE == kDual && OX == 4 && METHOD != PDS_METHOD_B);
+  constexpr int GQ = (MODE == kDual && !kEarly && (OX > 8 || METHOD == PDS_METHOD_B)) ? 1 : OX / 4;
+  const bool have_true = MODE == kDual && a.s.xtrue != nullptr;
+  float xv[GQ][4], xnv[GQ][4], tv[GQ][4], ob[GQ][4], xt[GQ][4], sn[GQ][4], so[GQ][4];
+  auto tail_loads = [&](int q0) {
+#pragma unroll
+    for (int j = 0; j < GQ; ++j) {
+      const int q = q0 + j;
+      if (4 * q >= nvalid) continue;
+      load4(a.s.x, q, xv[j]);
+      if constexpr (MODE == kDual) {
+        load4(a.s.xn, q, xnv[j]);
+        load4(a.s.t, q, tv[j]);            // same thread reads then writes its own elements
+        load4(a.s.obs, q, ob[j]);
+        if constexpr (METHOD == PDS_METHOD_B) {
+          load4(a.s.s_new, q, sn[j]);
+          load4(a.s.s_old, q, so[j]);
+        }
+        if (have_true) load4(a.s.xtrue, q, xt[j]);
+      }
+    }
+  };
+  if constexpr (kEarly) {
+    if (live) tail_loads(0);
+  }
+
   // stage the halo tile; the periodic wrap is one conditional add / subtract when the image is at least as large as the
   // halo reach (always, except for toy sizes)
   const bool easy = d.H >= RY + THR && d.W >= RX + TWR;
+  if ((RX & 3) == 0 && easy && (d.W & 3) == 0) {
+    // rows start 16-byte aligned (x0 and RX are multiples of 4) and a float4 never straddles the periodic seam: 128-bit loads,
+    // kBatch of them in flight per thread before the first shared-memory store (the staging phase is latency-bound)
+    constexpr int HC4 = HC / 4, NQ = HR * HC4, kBatch = 4;
+    for (int i0 = threadIdx.x; i0 < NQ; i0 += 256 * kBatch) {
+      float4 va[kBatch], vb[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int i = i0 + 256 * j;
+        if (i < NQ) {
+          const int hy = i / HC4, q = i - hy * HC4;
+          int gy = y0 - RY + hy, gx = x0 - RX + 4 * q;
+          gy += gy < 0 ? d.H : 0; gy -= gy >= d.H ? d.H : 0;
+          gx += gx < 0 ? d.W : 0; gx -= gx >= d.W ? d.W : 0;
+          const size_t g = pbase + (size_t)gy * d.W + gx;
+          if constexpr (MODE == kApply) va[j] = __ldg(reinterpret_cast<const float4*>(a.in + g));
+          else if constexpr (MODE == kPrimal) va[j] = __ldg(reinterpret_cast<const float4*>(a.s.t + g));
+          else {
+            va[j] = __ldg(reinterpret_cast<const float4*>(a.s.xn + g));
+            vb[j] = __ldg(reinterpret_cast<const float4*>(a.s.x + g));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int i = i0 + 256 * j;
+        if (i < NQ) {
+          const int hy = i / HC4, q = i - hy * HC4;
+          float4 v = va[j];
+          if constexpr (MODE == kDual) {
+            v.x = 2.f * va[j].x - vb[j].x; v.y = 2.f * va[j].y - vb[j].y;
+            v.z = 2.f * va[j].z - vb[j].z; v.w = 2.f * va[j].w - vb[j].w;
+          }
+          *reinterpret_cast<float4*>(tile + hy * PITCH + 4 * q) = v;
+        }
+      }
+    }
+  } else
   for (int idx = threadIdx.x; idx < HR * HC; idx += 256) {
     const int hy = idx / HC, hx = idx - hy * HC;
     int gy = y0 - RY + hy, gx = x0 - RX + hx;
@@ -187,7 +284,6 @@ __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__
   }
   __syncthreads();
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[OX];
 #pragma unroll
   for (int c = 0; c < OX; ++c) acc[c] = 0.f;
@@ -220,80 +316,50 @@ __global__ void __launch_bounds__(256, 3) blur_rt_kernel(const __grid_constant__
   float sg = 1.f, la = 0.f, lg4 = 0.f;
   if constexpr (MODE != kApply) {
     p = a.s.prm[b];
-    sg = item_sigma(METHOD, a.s.sums_prev, b, p);
+    sg = sg_s;
     la = p.lam * p.alpha;
     lg4 = 4.f * p.lam * p.g2;
   }
-  const int gy = y0 + lane, gx0 = x0 + OX * warp;
-  if (gy < d.H && gx0 < d.W) {
-    const size_t g0 = pbase + (size_t)gy * d.W + gx0;
-    const bool vec = ((d.W & 3) == 0);       // rows start 16-byte aligned and a float4 is never split by the edge
-    const int nvalid = (d.W - gx0) < OX ? (d.W - gx0) : OX;
-    // four outputs at a time (keeps the live registers of the pointwise tail small: occupancy matters for the staging loads)
-    auto load4 = [&](const float* base, int q, float (&r)[4]) {
-      if (vec) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(base + g0) + q);
-        r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
-      } else {
+  if (live) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) r[c] = (4 * q + c < nvalid) ? __ldg(base + g0 + 4 * q + c) : 0.f;
-      }
-    };
-    auto store4 = [&](float* base, int q, const float (&r)[4]) {
-      if (vec) {
-        *(reinterpret_cast<float4*>(base + g0) + q) = make_float4(r[0], r[1], r[2], r[3]);
-      } else {
+    for (int q0 = 0; q0 < OX / 4; q0 += GQ) {
+      if (4 * q0 >= nvalid) break;
+      if constexpr (MODE != kApply && !kEarly) tail_loads(q0);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) if (4 * q + c < nvalid) base[g0 + 4 * q + c] = r[c];
-      }
-    };
-    const bool have_true = MODE == kDual && a.s.xtrue != nullptr;
+      for (int j = 0; j < GQ; ++j) {
+        const int q = q0 + j;
+        if (4 * q >= nvalid) break;
+        if constexpr (MODE == kApply) {
+          const float r[4] = {acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]};
+          store4(a.out, q, r);
+        } else if constexpr (MODE == kPrimal) {
+          float r[4];
 #pragma unroll
-    for (int q = 0; q < OX / 4; ++q) {
-      if (4 * q >= nvalid) break;
-      float r[4] = {acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]};
-      if constexpr (MODE == kApply) {
-        store4(a.out, q, r);
-      } else if constexpr (MODE == kPrimal) {
-        float xv[4];
-        load4(a.s.x, q, xv);
+          for (int c = 0; c < 4; ++c) r[c] = fmaf(-p.g1 * sg, acc[4 * q + c], xv[j][c]);
+          store4(a.s.u, q, r);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) r[c] = fmaf(-p.g1 * sg, r[c], xv[c]);
-        store4(a.s.u, q, r);
-      } else {
-        float xv[4], xnv[4], tv[4], ob[4];
-        load4(a.s.xn, q, xnv);
-        load4(a.s.x, q, xv);
-        load4(a.s.t, q, tv);                 // same thread reads then writes its own elements
-        load4(a.s.obs, q, ob);
-        if constexpr (METHOD == PDS_METHOD_B) {
-          float sn[4], so[4];
-          load4(a.s.s_new, q, sn);
-          load4(a.s.s_old, q, so);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) r[c] += 2.f * sn[c] - so[c];
-        }
-        float xt[4] = {0.f, 0.f, 0.f, 0.f};
-        if (have_true) load4(a.s.xtrue, q, xt);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (4 * q + c >= nvalid) continue;
-          const float w = fmaf(p.g2, r[c], sg * tv[c]);
-          if constexpr (METHOD == PDS_METHOD_C) {
-            tv[c] = gkl_dual(w, ob[c], la, lg4);
-          } else {
-            tv[c] = fmaf(-p.g2, ob[c], w);
-            acc_t = fmaf(tv[c], tv[c], acc_t);
+          for (int c = 0; c < 4; ++c) {
+            if (4 * q + c >= nvalid) continue;
+            float r = acc[4 * q + c];
+            if constexpr (METHOD == PDS_METHOD_B) r += 2.f * sn[j][c] - so[j][c];
+            const float w = fmaf(p.g2, r, sg * tv[j][c]);
+            if constexpr (METHOD == PDS_METHOD_C) {
+              tv[j][c] = gkl_dual(w, ob[j][c], la, lg4);
+            } else {
+              tv[j][c] = fmaf(-p.g2, ob[j][c], w);
+              acc_t = fmaf(tv[j][c], tv[j][c], acc_t);
+            }
+            const float dx = xnv[j][c] - xv[j][c];
+            acc_dx = fmaf(dx, dx, acc_dx);
+            acc_x = fmaf(xv[j][c], xv[j][c], acc_x);
+            if (have_true) {
+              const float e = xnv[j][c] - xt[j][c];
+              acc_e = fmaf(e, e, acc_e);
+            }
           }
-          const float dx = xnv[c] - xv[c];
-          acc_dx = fmaf(dx, dx, acc_dx);
-          acc_x = fmaf(xv[c], xv[c], acc_x);
-          if (have_true) {
-            const float e = xnv[c] - xt[c];
-            acc_e = fmaf(e, e, acc_e);
-          }
+          store4(a.s.t, q, tv[j]);
         }
-        store4(a.s.t, q, tv);
       }
     }
   }
@@ -362,6 +428,8 @@ cudaError_t launch_rt(BlurArgs& a, const Dims& d, const BlurTaps& t, int which, 
       match = bits == kBlur1RowsHost[which][r];
     }
     if (match) {
+      if (big && t.debug_ox == 8)
+        return which == 0 ? launch_rt_ox<MODE, METHOD, RY, RX, 8, 1>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 8, 2>(a, d, st);
       if (which == 0) return big ? launch_rt_ox<MODE, METHOD, RY, RX, 16, 1>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 4, 1>(a, d, st);
       return big ? launch_rt_ox<MODE, METHOD, RY, RX, 16, 2>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 4, 2>(a, d, st);
     }
