@@ -237,6 +237,7 @@ struct FirstArgs {
   int clamp_in;
   int write_a8;           // see store_half_row (tc_common.cuh)
   int H, W, nimg, tiles_x, tiles_y, ntiles;
+  int dbg;                // timing probes of the tap-shifted kernel (wrong results): 1 = no activation stores, 2 = no proxy fence
 };
 
 template <int CIN>
@@ -444,19 +445,29 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 // row) — the trick of the body layers at K = 16 instead of 64.  The B rows of tap t hold
 //     [ w_hi(c) | w_hi(c) | w_lo(c) | bias as three fp16 terms (centre tap only) | 0 .. ]
 // so one M=128, N=64, K=16 MMA per tap accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ bias): 9 MMAs per tile into ONE fp32
-// accumulator, no correction accumulator, no bias add in the epilogue.  Six producer warps write the 180 records of a tile
-// (one pixel per thread, loads issued three tiles ahead); sixteen epilogue warps in four groups drain four TMEM stages, so the
-// kernel is bound by writing 192 (or 256) bytes per pixel.
+// accumulator, no correction accumulator, no bias add in the epilogue.  The fp32 window is landed by TMA (one 16 x 18 x Cin box
+// per tile); two groups of three builder warps turn it into the 180 records of a tile; sixteen epilogue warps in four groups
+// drain four TMEM stages.
 // ---------------------------------------------------------------------------------------------
 namespace first2 {
 constexpr int kStagesA = 4, kAcc = 4;
-constexpr int kProdThreads = 192, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
+constexpr int kProdThreads = 192, kGrpThreads = 96, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
 constexpr int kWinPix = kHaloRows * kHaloPitch;                     // 180 records per tile
 constexpr uint32_t kChunkPlane = kWinPix * 16;                      // 2880 bytes: K-slots 0-7 (plane 0) / 8-15 (plane 1) of every record
 constexpr uint32_t kStageBytes = 2 * kChunkPlane;
 constexpr uint32_t kWTap = 2 * 64 * 16, kWBytesF2 = 9 * kWTap;      // per tap: [chunk][oc][8 halves]
-constexpr uint32_t kOffA2 = kWBytesF2, kOffBar2 = kOffA2 + kStagesA * kStageBytes;
-constexpr uint32_t kSmemBytesF2 = kOffBar2 + 256 + 128;
+constexpr int kStg = 4, kBoxW = 16, kBoxX = 3;                       // input-window ring.  The box starts 4 pixels left of the tile and is 16 wide:
+                                                                     // TMA wants the innermost start coordinate and extent in 16-byte multiples
+                                                                     // (measured: tools/probe/tma_f32_probe.cu — x0 = 7 is an illegal instruction, 8 is fine)
+template <int CIN> struct Stg {
+  static constexpr uint32_t kBytes = (uint32_t)(CIN * kHaloRows * kBoxW * 4);
+  static constexpr uint32_t kSlot = (kBytes + 127u) & ~127u;
+};
+constexpr uint32_t kOffA2 = kWBytesF2, kOffStg2 = kOffA2 + kStagesA * kStageBytes, kOffBar2 = kOffStg2 + kStg * Stg<3>::kSlot;
+constexpr uint32_t kOffWst2 = kOffBar2 + 256;                        // per epilogue warp: 32 rows x 128 B (plane 0) + 32 x 128 B (plane 1)
+constexpr uint32_t kSmemBytesF2 = kOffWst2 + 4 * kAcc * 8192 + 128;
+static_assert(kOffWst2 % 128 == 0, "staging rows are 128-byte aligned");
+static_assert(kOffStg2 % 128 == 0, "TMA destination alignment");
 constexpr uint32_t kIdescF2 = kIdescBase | ((64u >> 3) << 17);
 static_assert(kOffA2 % 16 == 0 && kStageBytes % 16 == 0 && kOffBar2 % 8 == 0, "alignment");
 
@@ -466,9 +477,14 @@ __device__ __forceinline__ uint64_t desc_k_none(uint32_t addr, uint32_t lbo, uin
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | ((uint64_t)1 << 46);
 }
 
-// 32 channels [c0, c0+32) of one pixel from ONE accumulator that already holds the bias: LeakyReLU, then the stores of
-// store_half_row (tc_common.cuh): fp16(v) | e4m3(fp16(v)) (if write_a8) | e4m3((v - fp16(v)) 2^10)
-__device__ __forceinline__ void store_half_row1(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d)[32], int c0, float slope, int write_a8) {
+// 32 channels [c0, c0+32) of one pixel from ONE accumulator that already holds the bias: LeakyReLU, then the three encodings of
+// store_half_row (tc_common.cuh) — fp16(v) | e4m3(fp16(v)) (if write_a8) | e4m3((v - fp16(v)) 2^10) — written to the warp's
+// staging rows in shared memory (row = lane = pixel, 16-byte chunk c of a 128-byte row at c ^ (lane & 7): conflict-free both ways).
+// The warp then copies the rows out with every store instruction covering whole 128-byte lines (flush_rows below): with each
+// thread storing its own pixel's 32-byte pieces directly, a warp-level store touches 32 different lines, and the L1 store-request
+// rate — 768 requests per tile — was what bound this kernel (probe with consecutive addresses: 0.70 -> 0.45 ms per launch).
+__device__ __forceinline__ void stage_half_row1(uint32_t row_p0, uint32_t row_p1, int lane, const uint32_t (&d)[32], int half, float slope,
+                                                int write_a8) {
   uint32_t a8[8], l8[8];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -486,7 +502,12 @@ __device__ __forceinline__ void store_half_row1(__half* dst_p0, uint8_t* dst_p1,
       l[2 * k] = (v0 - hf.x) * kActLoScale;
       l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
     }
-    st_global_256(dst_p0 + c0 + q * 16, hi);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t chunk = (uint32_t)((half * 4 + q * 2 + k) ^ (lane & 7));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_p0 + chunk * 16u), "r"(hi[4 * k]), "r"(hi[4 * k + 1]), "r"(hi[4 * k + 2]),
+                   "r"(hi[4 * k + 3]) : "memory");
+    }
     if (write_a8) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) a8[q * 4 + k] = e4m3x2_from_f16x2(hi[2 * k]) | (e4m3x2_from_f16x2(hi[2 * k + 1]) << 16);
@@ -494,25 +515,65 @@ __device__ __forceinline__ void store_half_row1(__half* dst_p0, uint8_t* dst_p1,
 #pragma unroll
     for (int k = 0; k < 4; ++k) l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
   }
-  if (write_a8) st_global_256(dst_p1 + c0, a8);
-  st_global_256(dst_p1 + 64 + c0, l8);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (write_a8) {
+      const uint32_t ca = (uint32_t)((half * 2 + k) ^ (lane & 7));
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_p1 + ca * 16u), "r"(a8[4 * k]), "r"(a8[4 * k + 1]), "r"(a8[4 * k + 2]),
+                   "r"(a8[4 * k + 3]) : "memory");
+    }
+    const uint32_t cl = (uint32_t)((4 + half * 2 + k) ^ (lane & 7));
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_p1 + cl * 16u), "r"(l8[4 * k]), "r"(l8[4 * k + 1]), "r"(l8[4 * k + 2]),
+                 "r"(l8[4 * k + 3]) : "memory");
+  }
+}
+
+// Copies chunks [C0, 8) of the warp's 32 staged pixel rows to global memory: lane -> (pixel, 16-byte chunk), 32 / (8 - C0) pixels per
+// instruction; the pixels of a tile row are consecutive in memory, so an instruction writes 512 contiguous bytes (C0 = 0).
+template <int C0>
+__device__ __forceinline__ void flush_rows(uint32_t stage, uint8_t* plane, int lane, int q, int y0, int x0, int H, int W) {
+  constexpr int NC = 8 - C0, PPI = 32 / NC;              // chunks per pixel row that are stored, pixels per instruction
+#pragma unroll
+  for (int j = 0; j < 32 / PPI; ++j) {
+    const int r = j * PPI + lane / NC, c = C0 + lane % NC;
+    const int m = q * 32 + r;
+    const int y = y0 + (m >> 3), x = x0 + (m & 7);
+    uint32_t v0, v1, v2, v3;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                 : "r"(stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) * 16)) : "memory");
+    if (y < H && x < W)
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(plane + ((size_t)y * W + x) * 128 + c * 16), "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+                   : "memory");
+  }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(first::FirstArgs a) {
+__global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid_constant__ CUtensorMap tmap_in, first::FirstArgs a) {
   static_assert(3 * CIN + 3 <= 16, "K-slots of one record");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
   const uint32_t sW = base, sA = base + kOffA2, sBar = base + kOffBar2;
-  // barriers: fullA[4] @0, emptyA[4] @32, wfull @64, tfull[4] @72, tempty[4] @104, tmem slot @136
+  // barriers: fullA[4] @0, emptyA[4] @32, wfull @64, tfull[4] @72, tempty[4] @104, tmem slot @136, stgfull[4] @144, stgempty[4] @176
   const uint32_t bFull = sBar, bEmpty = sBar + 32, bW = sBar + 64, bTFull = sBar + 72, bTEmpty = sBar + 104, sTmemSlot = sBar + 136;
+  const uint32_t bSFull = sBar + 144, bSEmpty = sBar + 176, sStg = base + kOffStg2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStagesA; ++i) {
-      mbar_init(bFull + 8 * i, kProdThreads);      // every producer thread arrives after its record is written
+      mbar_init(bFull + 8 * i, kGrpThreads);       // every thread of the builder group arrives after its records are written
       mbar_init(bEmpty + 8 * i, 1);
     }
     mbar_init(bW, 1);
+    for (int i = 0; i < kStg; ++i) {
+      mbar_init(bSFull + 8 * i, 1);
+      mbar_init(bSEmpty + 8 * i, kGrpThreads / 32);
+    }
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_in) : "memory");
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(bTFull + 8 * i, 1);
       mbar_init(bTEmpty + 8 * i, 4);
@@ -531,75 +592,87 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(first::First
   const size_t hw = (size_t)a.H * a.W;
 
   if (warp < kMmaWarp2) {
-    // ------------------------------------------------------------ record producers: thread p = window pixel p (p < 180)
+    // ------------------------------------------------------------ record builders: thread p = window pixel p (p < 180).  The
+    // window itself (Cin x 18 x 16 floats, zero-filled outside the image = the convolution's padding) is landed by TMA, so no
+    // thread of this kernel has a global load in flight when it reaches the proxy fence below (fence.proxy.async = MEMBAR +
+    // FENCE.VIEW.ASYNC: with register-prefetched loads every tile waited out a DRAM round trip there).
     if (threadIdx.x == 0) {
       mbar_expect_tx(bW, kWBytesF2);
       bulk_load(sW, a.w_img, kWBytesF2, bW);
     }
-    const int p = threadIdx.x;
-    const bool active = p < kWinPix;
-    const int hy = p / kHaloPitch, hx = p - hy * kHaloPitch;
-    constexpr int kDepth = 3;
-    float pre[kDepth][CIN];
-    bool inside[kDepth];
-    auto fetch = [&](int tile, float (&r)[CIN], bool& in_img) {
-      const int img = tile / per_img, rem = tile - img * per_img;
-      const int gy = (rem / a.tiles_x) * kTileRows - 1 + hy, gx = (rem % a.tiles_x) * kTileCols - 1 + hx;
-      in_img = active && gy >= 0 && gy < a.H && gx >= 0 && gx < a.W;
+    // Two groups of three warps, group g builds the tiles with it % 2 == g (two records per thread): the proxy fence and the
+    // arrive are a serial chain per tile (ncu: half of a builder's time), so two tiles are in flight.
+    const int grp = warp / 3;
+    const int t = threadIdx.x - grp * kGrpThreads;
+    float* const stg_base = reinterpret_cast<float*>(smem_raw + kOffStg2);
+    int off[2];
+    bool active[2];
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) r[c] = in_img ? __ldg(a.in + ((size_t)(img * CIN + c) * a.H + gy) * a.W + gx) : 0.f;
-    };
-    const int tstep = (int)gridDim.x;
-#pragma unroll
-    for (int dd = 0; dd < kDepth; ++dd) {
-      inside[dd] = false;
-      const int t0 = blockIdx.x + dd * tstep;
-      if (t0 < a.ntiles) fetch(t0, pre[dd], inside[dd]);
+    for (int j = 0; j < 2; ++j) {
+      const int p = t + j * kGrpThreads;
+      active[j] = p < kWinPix;
+      const int hy = p / kHaloPitch, hx = p - hy * kHaloPitch;
+      off[j] = hy * kBoxW + hx + kBoxX;
     }
-    int it = 0;
-    for (int tile0 = blockIdx.x; tile0 < a.ntiles; tile0 += kDepth * tstep) {
+    for (int it = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += 2 * (int)gridDim.x, it += 2) {
+      const uint32_t slot = it % kStg;
+      mbar_wait(bSFull + 8 * slot, (uint32_t)((it / kStg) & 1));
+      float v[2][CIN];
 #pragma unroll
-      for (int dd = 0; dd < kDepth; ++dd, ++it) {
-        const int tile = tile0 + dd * tstep;
-        if (tile >= a.ntiles) break;
-        // fp16 hi / lo split of the (clamped, denoiser.py:40) input; pixels outside the image are all-zero records = the
-        // convolution's zero padding (their "1" slots only ever meet zero weights: the bias sits in the centre tap)
-        uint32_t rec[8];
-        {
-          __half h16[16];
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
-          for (int k = 0; k < 16; ++k) h16[k] = __float2half_rn(0.f);
-          if (inside[dd]) {
+        for (int c = 0; c < CIN; ++c) v[j][c] = active[j] ? stg_base[slot * (Stg<CIN>::kSlot / 4) + c * (kHaloRows * kBoxW) + off[j]] : 0.f;
+      // fp16 hi / lo split of the (clamped, denoiser.py:40) input.  The "1" slots are set in every record: they only meet
+      // non-zero weights (the bias) in the centre tap, whose pixel is the output pixel itself.
+      uint32_t rec[2][8];
 #pragma unroll
-            for (int c = 0; c < CIN; ++c) {
-              const float v = a.clamp_in ? fminf(fmaxf(pre[dd][c], 0.f), 1.f) : pre[dd][c];
-              const __half hi = __float2half_rn(v);
-              const __half lo = __float2half_rn(v - __half2float(hi));
-              h16[c] = hi;
-              h16[CIN + c] = lo;
-              h16[2 * CIN + c] = hi;
-            }
+      for (int j = 0; j < 2; ++j) {
+        __half h16[16];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) h16[3 * CIN + k] = __float2half_rn(1.f);
-          }
+        for (int k2 = 0; k2 < 16; ++k2) h16[k2] = __float2half_rn(0.f);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            rec[k] = (uint32_t)__half_as_ushort(h16[2 * k]) | ((uint32_t)__half_as_ushort(h16[2 * k + 1]) << 16);
+        for (int c = 0; c < CIN; ++c) {
+          const float x = a.clamp_in ? fminf(fmaxf(v[j][c], 0.f), 1.f) : v[j][c];
+          const __half hi = __float2half_rn(x);
+          const __half lo = __float2half_rn(x - __half2float(hi));
+          h16[c] = hi;
+          h16[CIN + c] = lo;
+          h16[2 * CIN + c] = hi;
         }
-        const uint32_t stage = it % kStagesA, use = it / kStagesA;
-        mbar_wait(bEmpty + 8 * stage, (use & 1) ^ 1);
-        if (active) {
-          const uint32_t dst = sA + stage * kStageBytes + (uint32_t)p * 16u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(rec[0]), "r"(rec[1]), "r"(rec[2]), "r"(rec[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kChunkPlane), "r"(rec[4]), "r"(rec[5]), "r"(rec[6]), "r"(rec[7]) : "memory");
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2) h16[3 * CIN + k2] = __float2half_rn(1.f);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2)
+          rec[j][k2] = (uint32_t)__half_as_ushort(h16[2 * k2]) | ((uint32_t)__half_as_ushort(h16[2 * k2 + 1]) << 16);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bSEmpty + 8 * slot);          // the window slot may be refilled
+      const uint32_t stage = it % kStagesA, use = it / kStagesA;
+      mbar_wait(bEmpty + 8 * stage, (use & 1) ^ 1);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (active[j]) {
+          const uint32_t dst = sA + stage * kStageBytes + (uint32_t)(t + j * kGrpThreads) * 16u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(rec[j][0]), "r"(rec[j][1]), "r"(rec[j][2]), "r"(rec[j][3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + kChunkPlane), "r"(rec[j][4]), "r"(rec[j][5]), "r"(rec[j][6]), "r"(rec[j][7]) : "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        mbar_arrive(bFull + 8 * stage);
-        // prefetch for the tile kDepth rounds ahead — after the releasing arrive, whose MEMBAR would otherwise wait for these loads
-        inside[dd] = false;
-        if (tile + kDepth * tstep < a.ntiles) fetch(tile + kDepth * tstep, pre[dd], inside[dd]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(bFull + 8 * stage);
+    }
+  } else if (warp == kMmaWarp2 + 1) {
+    // ------------------------------------------------------------ TMA producer: one (16 x 18 x Cin) box per tile
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
+        const int img = tile / per_img, rem = tile - img * per_img;
+        const int y0 = (rem / a.tiles_x) * kTileRows - 1, x0 = (rem % a.tiles_x) * kTileCols - 1 - kBoxX;
+        const uint32_t slot = it % kStg;
+        mbar_wait(bSEmpty + 8 * slot, (uint32_t)(((it / kStg) & 1) ^ 1));
+        mbar_expect_tx(bSFull + 8 * slot, Stg<CIN>::kBytes);
+        tma_load_4d(sStg + slot * Stg<CIN>::kSlot, &tmap_in, bSFull + 8 * slot, x0, y0, 0, img);
       }
     }
+    __syncwarp();
   } else if (warp == kMmaWarp2) {
     // ------------------------------------------------------------ MMA issuer: nine K=16 MMAs per tile, one per tap
     mbar_wait(bW, 0);
@@ -628,25 +701,20 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(first::First
     // with it % 4 == g = accumulator stage g
     const int q = warp & 3;                               // TMEM lane quadrant this warp may read
     const int grp = (warp - kEpiWarp0) >> 2;
-    const int m = q * 32 + lane;
-    const int ty = m >> 3, tx = m & 7;
     int it = grp;
     for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += kAcc * gridDim.x, it += kAcc) {
       const int img = tile / per_img, rem = tile - img * per_img;
-      const int y = (rem / a.tiles_x) * kTileRows + ty, x = (rem % a.tiles_x) * kTileCols + tx;
       const uint32_t acc = (uint32_t)grp;
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it / kAcc) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u;
-      const bool st = y < a.H && x < a.W;
-      const size_t pix = (size_t)y * a.W + x;
-      __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
-      uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
+      const uint32_t wst = base + kOffWst2 + (uint32_t)(warp - kEpiWarp0) * 8192u;
+      const uint32_t row_p0 = wst + (uint32_t)lane * 128u, row_p1 = row_p0 + 4096u;
       {
         uint32_t r0[32];
         tmem_ld32(taddr, r0);
         tmem_ld_wait();
-        if (st) store_half_row1(o_p0, o_p1, r0, 0, a.slope, a.write_a8);
+        stage_half_row1(row_p0, row_p1, lane, r0, 0, a.slope, a.write_a8);
       }
       {
         uint32_t r1[32];
@@ -655,8 +723,18 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(first::First
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
-        if (st) store_half_row1(o_p0, o_p1, r1, 32, a.slope, a.write_a8);
+        stage_half_row1(row_p0, row_p1, lane, r1, 1, a.slope, a.write_a8);
       }
+      __syncwarp();
+      if (!(a.dbg & 1)) {
+        const int ty0 = (rem / a.tiles_x) * kTileRows, tx0 = (rem % a.tiles_x) * kTileCols;
+        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out + ((size_t)img * 2 + 0) * hw * 64);
+        uint8_t* p1 = reinterpret_cast<uint8_t*>(a.out + ((size_t)img * 2 + 1) * hw * 64);
+        flush_rows<0>(wst, p0, lane, q, ty0, tx0, a.H, a.W);
+        if (a.write_a8) flush_rows<0>(wst + 4096u, p1, lane, q, ty0, tx0, a.H, a.W);
+        else flush_rows<4>(wst + 4096u, p1, lane, q, ty0, tx0, a.H, a.W);
+      }
+      __syncwarp();                                     // the staging rows are rewritten by the next tile
     }
   }
   tc_fence_before();
@@ -1140,6 +1218,28 @@ int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W, int box_
   return 0;
 }
 
+// fp32 planar network input (nimg, C, H, W) as a 4-D tensor map with a (16 x 18 x C x 1) box, cached per (pointer, planes, C)
+const CUtensorMap* plan_input_map(TcPlan* plan, const float* in, int planes, int C) {
+  for (auto& e : plan->in_maps)
+    if (e.ptr == in && e.planes == planes && e.C == C) return &e.map;
+  EncodeTiledFn enc = get_encode();
+  if (enc == nullptr) return nullptr;
+  TcPlan::InMap e{};
+  e.ptr = in;
+  e.planes = planes;
+  e.C = C;
+  const cuuint64_t dims[4] = {(cuuint64_t)plan->W, (cuuint64_t)plan->H, (cuuint64_t)C, (cuuint64_t)(planes / C)};
+  const cuuint64_t strides[3] = {(cuuint64_t)plan->W * 4, (cuuint64_t)plan->H * plan->W * 4, (cuuint64_t)C * plan->H * plan->W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)first2::kBoxW, (cuuint32_t)kHaloRows, (cuuint32_t)C, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return nullptr;
+  if (plan->in_maps.size() >= 32) plan->in_maps.erase(plan->in_maps.begin());
+  plan->in_maps.push_back(e);
+  return &plan->in_maps.back().map;
+}
+
 }  // namespace
 
 
@@ -1192,6 +1292,8 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   *out = p;
   return 0;
 }
+
+void tc_plan_set_first_dbg(TcPlan* p, int bits) { p->first_dbg = bits; }
 
 void tc_plan_destroy(TcPlan* p) {
   if (!p) return;
@@ -1256,12 +1358,17 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
   a.tiles_y = (plan->H + kTileRows - 1) / kTileRows;
   a.ntiles = a.tiles_x * a.tiles_y * nimg;
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  if (!im2col) {
-    if (C == 1) first2::conv_first2_kernel<1><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(a);
-    else if (C == 3) first2::conv_first2_kernel<3><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(a);
-    else return cudaErrorInvalidValue;
+  // the tap-shifted kernel lands its input windows by TMA: rows must be 16-byte multiples (W % 4 == 0) from a 16-byte aligned base;
+  // other shapes take the im2col kernel
+  if (!im2col && (plan->W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (C == 1 || C == 3)) {
+    const CUtensorMap* m = plan_input_map(plan, in, nimg * C, C);
+    a.dbg = plan->first_dbg;
+    if (m == nullptr) return cudaErrorInvalidValue;
+    if (C == 1) first2::conv_first2_kernel<1><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a);
+    else first2::conv_first2_kernel<3><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a);
     return cudaGetLastError();
   }
+  a.w_img = L.w_first_tc;
   if (C == 1) first::conv_first_tc_kernel<1><<<grid, first::kThreadsF, first::kSmemBytesF, st>>>(a);
   else if (C == 3) first::conv_first_tc_kernel<3><<<grid, first::kThreadsF, first::kSmemBytesF, st>>>(a);
   else return cudaErrorInvalidValue;

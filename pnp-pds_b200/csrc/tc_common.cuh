@@ -35,6 +35,10 @@ struct TcPlan {
   uint32_t chain_epoch = 0;
   size_t chain_bytes = 0;
   unsigned long long* chain_trace = nullptr;   // debug timeline buffer (pds_debug_chain_trace), normally null
+  // first layer (tap-shifted kernel): tensor maps over the fp32 network input, one per (pointer, planes) seen
+  struct InMap { const float* ptr; int planes, C; CUtensorMap map; };
+  std::vector<InMap> in_maps;
+  int first_dbg = 0;                    // timing probes of the first layer (tc_variant bits 16 / 17, wrong results by design)
 };
 int chain_setup();
 int tc_plan_set_chain(TcPlan* plan, const std::vector<ChainLayer>& layers);
