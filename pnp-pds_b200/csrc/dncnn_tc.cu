@@ -493,14 +493,15 @@ __device__ __forceinline__ void stage_half_row1(uint32_t row_p0, uint32_t row_p1
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = q * 16 + 2 * k;
-      float v0 = __uint_as_float(d[c]), v1 = __uint_as_float(d[c + 1]);
-      v0 = fmaxf(v0, v0 * slope);
-      v1 = fmaxf(v1, v1 * slope);
-      const __half2 hh = __floats2half2_rn(v0, v1);
-      const float2 hf = __half22float2(hh);
+      float2 v = make_float2(__uint_as_float(d[c]), __uint_as_float(d[c + 1]));
+      const float2 vs = mul2(v, make_float2(slope, slope));
+      v.x = fmaxf(v.x, vs.x);
+      v.y = fmaxf(v.y, vs.y);
+      const __half2 hh = __floats2half2_rn(v.x, v.y);
+      const float2 lo = mul2(sub2(v, __half22float2(hh)), make_float2(kActLoScale, kActLoScale));
       hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[2 * k] = (v0 - hf.x) * kActLoScale;
-      l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
+      l[2 * k] = lo.x;
+      l[2 * k + 1] = lo.y;
     }
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
@@ -528,23 +529,39 @@ __device__ __forceinline__ void stage_half_row1(uint32_t row_p0, uint32_t row_p1
   }
 }
 
-// Copies chunks [C0, 8) of the warp's 32 staged pixel rows to global memory: lane -> (pixel, 16-byte chunk), 32 / (8 - C0) pixels per
-// instruction; the pixels of a tile row are consecutive in memory, so an instruction writes 512 contiguous bytes (C0 = 0).
+// Copies chunks [C0, 8) of the warp's 32 staged pixel rows (a 4-row x 8-pixel piece of the tile) to global memory:
+// lane -> (pixel, 16-byte chunk), 32 / (8 - C0) pixels per instruction; the pixels of a tile row are consecutive in memory, so an
+// instruction writes 512 contiguous bytes (C0 = 0).  g0 = address of this lane's chunk in the piece's first row, row_bytes = W * 128;
+// full = the whole tile lies inside the image (no per-store bounds test).
 template <int C0>
-__device__ __forceinline__ void flush_rows(uint32_t stage, uint8_t* plane, int lane, int q, int y0, int x0, int H, int W) {
-  constexpr int NC = 8 - C0, PPI = 32 / NC;              // chunks per pixel row that are stored, pixels per instruction
+__device__ __forceinline__ void flush_rows(uint32_t stage, uint8_t* g0, size_t row_bytes, int lane, bool full, int rows_left, int cols_left) {
+  constexpr int NC = 8 - C0, PPI = 32 / NC, NI = 32 / PPI, JR = 8 / PPI;   // JR instructions per tile row
+  const int tx0 = lane / NC, c = C0 + lane % NC;
+  uint32_t v[NI][4];
 #pragma unroll
-  for (int j = 0; j < 32 / PPI; ++j) {
-    const int r = j * PPI + lane / NC, c = C0 + lane % NC;
-    const int m = q * 32 + r;
-    const int y = y0 + (m >> 3), x = x0 + (m & 7);
-    uint32_t v0, v1, v2, v3;
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
-                 : "r"(stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) * 16)) : "memory");
-    if (y < H && x < W)
-      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(plane + ((size_t)y * W + x) * 128 + c * 16), "r"(v0), "r"(v1), "r"(v2), "r"(v3)
+  for (int j = 0; j < NI; ++j) {                                // all shared-memory reads first: independent, latencies overlap
+    const int tx = tx0 + (j % JR) * PPI, r = (j / JR) * 8 + tx;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3])
+                 : "r"(stage + (uint32_t)r * 128u + (uint32_t)((c ^ tx) * 16)));
+  }
+#pragma unroll
+  for (int j = 0; j < NI; ++j) {
+    const int tx = tx0 + (j % JR) * PPI, ty = j / JR;
+    if (full || (ty < rows_left && tx < cols_left))
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + (size_t)ty * row_bytes + (size_t)((j % JR) * PPI) * 128), "r"(v[j][0]),
+                   "r"(v[j][1]), "r"(v[j][2]), "r"(v[j][3])
                    : "memory");
   }
+}
+
+// n / d for a divisor fixed per launch (round-up multiplier, Granlund-Montgomery): the tile -> (image, row, column) split is done by
+// every warp for every tile, and an integer division is ~25 instructions
+struct FastDiv {
+  uint32_t mul, sh1, sh2, d;
+};
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) {
+  const uint32_t t = __umulhi(f.mul, n);
+  return (t + ((n - t) >> f.sh1)) >> f.sh2;
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -554,7 +571,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid_constant__ CUtensorMap tmap_in, first::FirstArgs a) {
+__global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid_constant__ CUtensorMap tmap_in, first::FirstArgs a, FastDiv div_img,
+                                                                    FastDiv div_tx) {
   static_assert(3 * CIN + 3 <= 16, "K-slots of one record");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw);
@@ -664,8 +682,9 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
     if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-        const int img = tile / per_img, rem = tile - img * per_img;
-        const int y0 = (rem / a.tiles_x) * kTileRows - 1, x0 = (rem % a.tiles_x) * kTileCols - 1 - kBoxX;
+        const int img = (int)fdiv((uint32_t)tile, div_img), rem = tile - img * per_img;
+        const int trow = (int)fdiv((uint32_t)rem, div_tx);
+        const int y0 = trow * kTileRows - 1, x0 = (rem - trow * a.tiles_x) * kTileCols - 1 - kBoxX;
         const uint32_t slot = it % kStg;
         mbar_wait(bSEmpty + 8 * slot, (uint32_t)(((it / kStg) & 1) ^ 1));
         mbar_expect_tx(bSFull + 8 * slot, Stg<CIN>::kBytes);
@@ -703,7 +722,6 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
     const int grp = (warp - kEpiWarp0) >> 2;
     int it = grp;
     for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += kAcc * gridDim.x, it += kAcc) {
-      const int img = tile / per_img, rem = tile - img * per_img;
       const uint32_t acc = (uint32_t)grp;
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it / kAcc) & 1));
       tc_fence_after();
@@ -727,12 +745,16 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
       }
       __syncwarp();
       if (!(a.dbg & 1)) {
-        const int ty0 = (rem / a.tiles_x) * kTileRows, tx0 = (rem % a.tiles_x) * kTileCols;
-        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out + ((size_t)img * 2 + 0) * hw * 64);
-        uint8_t* p1 = reinterpret_cast<uint8_t*>(a.out + ((size_t)img * 2 + 1) * hw * 64);
-        flush_rows<0>(wst, p0, lane, q, ty0, tx0, a.H, a.W);
-        if (a.write_a8) flush_rows<0>(wst + 4096u, p1, lane, q, ty0, tx0, a.H, a.W);
-        else flush_rows<4>(wst + 4096u, p1, lane, q, ty0, tx0, a.H, a.W);
+        const int img = (int)fdiv((uint32_t)tile, div_img), rem = tile - img * per_img;
+        const int trow = (int)fdiv((uint32_t)rem, div_tx);
+        const int ty0 = trow * kTileRows + q * 4, tx0 = (rem - trow * a.tiles_x) * kTileCols;   // this warp's 4 x 8 piece
+        const bool full = ty0 + 4 <= a.H && tx0 + kTileCols <= a.W;
+        const size_t row_bytes = (size_t)a.W * 128;
+        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out) + ((size_t)img * 2 * hw + (size_t)ty0 * a.W + tx0) * 128;
+        uint8_t* p1 = p0 + hw * 128;
+        flush_rows<0>(wst, p0 + (lane >> 3) * 128 + (lane & 7) * 16, row_bytes, lane, full, a.H - ty0, a.W - tx0);
+        if (a.write_a8) flush_rows<0>(wst + 4096u, p1 + (lane >> 3) * 128 + (lane & 7) * 16, row_bytes, lane, full, a.H - ty0, a.W - tx0);
+        else flush_rows<4>(wst + 4096u, p1 + (lane >> 2) * 128 + (4 + (lane & 3)) * 16, row_bytes, lane, full, a.H - ty0, a.W - tx0);
       }
       __syncwarp();                                     // the staging rows are rewritten by the next tile
     }
@@ -1218,6 +1240,17 @@ int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W, int box_
   return 0;
 }
 
+first2::FastDiv make_fastdiv(uint32_t d) {
+  first2::FastDiv f{};
+  f.d = d;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;                       // ceil(log2 d)
+  f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.sh1 = l < 1 ? l : 1;
+  f.sh2 = l < 1 ? 0 : l - 1;
+  return f;
+}
+
 // fp32 planar network input (nimg, C, H, W) as a 4-D tensor map with a (16 x 18 x C x 1) box, cached per (pointer, planes, C)
 const CUtensorMap* plan_input_map(TcPlan* plan, const float* in, int planes, int C) {
   for (auto& e : plan->in_maps)
@@ -1364,8 +1397,9 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
     const CUtensorMap* m = plan_input_map(plan, in, nimg * C, C);
     a.dbg = plan->first_dbg;
     if (m == nullptr) return cudaErrorInvalidValue;
-    if (C == 1) first2::conv_first2_kernel<1><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a);
-    else first2::conv_first2_kernel<3><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a);
+    const first2::FastDiv di = make_fastdiv((uint32_t)(a.tiles_x * a.tiles_y)), dx = make_fastdiv((uint32_t)a.tiles_x);
+    if (C == 1) first2::conv_first2_kernel<1><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a, di, dx);
+    else first2::conv_first2_kernel<3><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a, di, dx);
     return cudaGetLastError();
   }
   a.w_img = L.w_first_tc;

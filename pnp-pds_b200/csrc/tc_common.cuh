@@ -170,6 +170,27 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&v)[8]) {
                : "memory");
 }
 
+// Packed fp32 pairs (FMUL2 / FADD2, sm_100): one issue slot for two lanes of the epilogue's elementwise maths.  Same roundings as
+// the scalar forms.
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+
 constexpr float kActLoScale = 1024.f;     // 2^10: e4m3(a_lo * 2^10) stays finite for |a| < 448 (a_lo <= 2^-11 * 2^ceil(log2|a|))
 
 __device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
