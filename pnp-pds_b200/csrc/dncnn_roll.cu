@@ -44,6 +44,7 @@ struct RollArgs {
   int npairs_x;           // 256-pixel strip pairs per image row
   int total_rows;         // nimg * npairs_x * H: rows of all strip-pair columns, column after column
   int rows_per_cluster;   // contiguous share of that sequence owned by one CTA pair
+  int dbg;                // timing probes of conv_roll_d_kernel's epilogue (wrong results): 1 = no activation stores, 2 = every warp-level store covers 1 KB of consecutive addresses
 };
 
 // The work of one CTA pair: rows [cid * rows_per_cluster, ...) of the global row sequence, cut into bands at the column
@@ -423,12 +424,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreadsD, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) two::mbar_arrive_cluster(tempty0 + 8 * blk);      // block released before any arithmetic or store
-        if (x < a.W) {
+        if (x < a.W && !(a.dbg & 1)) {
           const size_t pix = (size_t)(yb + jr) * a.W + x;
           __half* o_p0 = a.out + (((size_t)img * 2 + 0) * hw + pix) * 64;
           uint8_t* o_p1 = reinterpret_cast<uint8_t*>(a.out + (((size_t)img * 2 + 1) * hw + pix) * 64);
-          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale, a.write_a8);
-          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale, a.write_a8);
+          uint32_t cs = 32;
+          if (a.dbg & 2) {            // same 4 KB piece per warp and plane, lane-linear inside it
+            o_p0 = o_p0 - (size_t)lane * 64 + lane * 16;
+            o_p1 = o_p1 - (size_t)lane * 128 + lane * 32;
+            cs = 1024;
+          }
+          store_half_row(o_p0, o_p1, r0, r2, bias_s, 0, a.slope, a.lo_scale, a.write_a8, cs);
+          store_half_row(o_p0, o_p1, r1, r3, bias_s, 32, a.slope, a.lo_scale, a.write_a8, cs);
         }
       }
     }
@@ -571,6 +578,7 @@ cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_ro
   a.in = plan->act[in_buf];
   a.out = plan->act[in_buf ^ 1];
   a.write_a8 = write_a8;
+  a.dbg = plan->first_dbg;
   a.slope = slope;
   a.lo_scale = L.lo_scale;
   a.H = plan->H;

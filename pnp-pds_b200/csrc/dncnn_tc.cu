@@ -451,16 +451,21 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 // ---------------------------------------------------------------------------------------------
 namespace first2 {
 constexpr int kStagesA = 4, kAcc = 4;
-constexpr int kProdThreads = 192, kGrpThreads = 96, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
-constexpr int kWinPix = kHaloRows * kHaloPitch;                     // 180 records per tile
-constexpr uint32_t kChunkPlane = kWinPix * 16;                      // 2880 bytes: K-slots 0-7 (plane 0) / 8-15 (plane 1) of every record
+constexpr int kBuilders = 4, kGrpThreads = 32, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
+// Tile = 128 consecutive pixels of ONE image row (M = 128): its activations are 16 KB of consecutive addresses in plane 0 (DRAM
+// pages, full lines), and the window is 3 rows x 130 pixels = 3 x Cin TMA rows of 544 bytes.  (With 16 x 8-pixel tiles the stores
+// were 1 KB runs 128 KB apart and the kernel stopped at 4.2 TB/s; the window was 54 TMA rows of 64 bytes.)
+constexpr int kTW = 128, kWinRows = 3, kWinPitch = kTW + 2;
+constexpr int kWinPix = kWinRows * kWinPitch;                       // 390 records per tile
+constexpr int kRecPerThread = (kWinPix + 31) / 32;                  // 13
+constexpr uint32_t kChunkPlane = kWinPix * 16;                      // 6240 bytes: K-slots 0-7 (plane 0) / 8-15 (plane 1) of every record
 constexpr uint32_t kStageBytes = 2 * kChunkPlane;
 constexpr uint32_t kWTap = 2 * 64 * 16, kWBytesF2 = 9 * kWTap;      // per tap: [chunk][oc][8 halves]
-constexpr int kStg = 4, kBoxW = 16, kBoxX = 3;                       // input-window ring.  The box starts 4 pixels left of the tile and is 16 wide:
+constexpr int kStg = 4, kBoxW = kTW + 8, kBoxX = 3;                  // input-window ring.  The box starts 4 pixels left of the tile and is 136 wide:
                                                                      // TMA wants the innermost start coordinate and extent in 16-byte multiples
                                                                      // (measured: tools/probe/tma_f32_probe.cu — x0 = 7 is an illegal instruction, 8 is fine)
 template <int CIN> struct Stg {
-  static constexpr uint32_t kBytes = (uint32_t)(CIN * kHaloRows * kBoxW * 4);
+  static constexpr uint32_t kBytes = (uint32_t)(CIN * kWinRows * kBoxW * 4);
   static constexpr uint32_t kSlot = (kBytes + 127u) & ~127u;
 };
 constexpr uint32_t kOffA2 = kWBytesF2, kOffStg2 = kOffA2 + kStagesA * kStageBytes, kOffBar2 = kOffStg2 + kStg * Stg<3>::kSlot;
@@ -529,27 +534,25 @@ __device__ __forceinline__ void stage_half_row1(uint32_t row_p0, uint32_t row_p1
   }
 }
 
-// Copies chunks [C0, 8) of the warp's 32 staged pixel rows (a 4-row x 8-pixel piece of the tile) to global memory:
-// lane -> (pixel, 16-byte chunk), 32 / (8 - C0) pixels per instruction; the pixels of a tile row are consecutive in memory, so an
-// instruction writes 512 contiguous bytes (C0 = 0).  g0 = address of this lane's chunk in the piece's first row, row_bytes = W * 128;
-// full = the whole tile lies inside the image (no per-store bounds test).
+// Copies chunks [C0, 8) of the warp's 32 staged pixel rows (32 consecutive pixels of an image row) to global memory:
+// lane -> (pixel, 16-byte chunk), 32 / (8 - C0) pixels per instruction, every instruction writes whole lines of consecutive
+// addresses (512 bytes for C0 = 0).  g0 = address of this lane's chunk in the first instruction; left = pixels inside the image.
 template <int C0>
-__device__ __forceinline__ void flush_rows(uint32_t stage, uint8_t* g0, size_t row_bytes, int lane, bool full, int rows_left, int cols_left) {
-  constexpr int NC = 8 - C0, PPI = 32 / NC, NI = 32 / PPI, JR = 8 / PPI;   // JR instructions per tile row
-  const int tx0 = lane / NC, c = C0 + lane % NC;
+__device__ __forceinline__ void flush_rows(uint32_t stage, uint8_t* g0, int lane, int left) {
+  constexpr int NC = 8 - C0, PPI = 32 / NC, NI = 32 / PPI;
+  const int px0 = lane / NC, c = C0 + lane % NC;
   uint32_t v[NI][4];
 #pragma unroll
   for (int j = 0; j < NI; ++j) {                                // all shared-memory reads first: independent, latencies overlap
-    const int tx = tx0 + (j % JR) * PPI, r = (j / JR) * 8 + tx;
+    const int r = j * PPI + px0;
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j][0]), "=r"(v[j][1]), "=r"(v[j][2]), "=r"(v[j][3])
-                 : "r"(stage + (uint32_t)r * 128u + (uint32_t)((c ^ tx) * 16)));
+                 : "r"(stage + (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) * 16)));
   }
 #pragma unroll
   for (int j = 0; j < NI; ++j) {
-    const int tx = tx0 + (j % JR) * PPI, ty = j / JR;
-    if (full || (ty < rows_left && tx < cols_left))
-      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + (size_t)ty * row_bytes + (size_t)((j % JR) * PPI) * 128), "r"(v[j][0]),
-                   "r"(v[j][1]), "r"(v[j][2]), "r"(v[j][3])
+    if (j * PPI + px0 < left)
+      asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(g0 + (size_t)(j * PPI) * 128), "r"(v[j][0]), "r"(v[j][1]), "r"(v[j][2]),
+                   "r"(v[j][3])
                    : "memory");
   }
 }
@@ -609,42 +612,43 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
   const int per_img = a.tiles_x * a.tiles_y;
   const size_t hw = (size_t)a.H * a.W;
 
-  if (warp < kMmaWarp2) {
-    // ------------------------------------------------------------ record builders: thread p = window pixel p (p < 180).  The
-    // window itself (Cin x 18 x 16 floats, zero-filled outside the image = the convolution's padding) is landed by TMA, so no
-    // thread of this kernel has a global load in flight when it reaches the proxy fence below (fence.proxy.async = MEMBAR +
-    // FENCE.VIEW.ASYNC: with register-prefetched loads every tile waited out a DRAM round trip there).
+  if (warp < kBuilders) {
+    // ------------------------------------------------------------ record builders.  The window itself (Cin x 3 x 136 floats,
+    // zero-filled outside the image = the convolution's padding) is landed by TMA, so no thread of this kernel has a global load
+    // in flight when it reaches the proxy fence below (fence.proxy.async = MEMBAR + FENCE.VIEW.ASYNC: with register-prefetched
+    // loads every tile waited out a DRAM round trip there).  Four builder warps, warp g builds the tiles with it % 4 == g (13
+    // records per lane): a tile's build is one serial chain (wait for the window, build, wait for a free stage, store, proxy
+    // fence, arrive) whose hand-offs cost more than its arithmetic — measured with the epilogue switched off: two groups of
+    // three warps delivered a tile every 1 120 cycles.
     if (threadIdx.x == 0) {
       mbar_expect_tx(bW, kWBytesF2);
       bulk_load(sW, a.w_img, kWBytesF2, bW);
     }
-    // Two groups of three warps, group g builds the tiles with it % 2 == g (two records per thread): the proxy fence and the
-    // arrive are a serial chain per tile (ncu: half of a builder's time), so two tiles are in flight.
-    const int grp = warp / 3;
-    const int t = threadIdx.x - grp * kGrpThreads;
+    const int grp = warp;
+    const int t = lane;
     float* const stg_base = reinterpret_cast<float*>(smem_raw + kOffStg2);
-    int off[2];
-    bool active[2];
+    int off[kRecPerThread];
+    bool active[kRecPerThread];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < kRecPerThread; ++j) {
       const int p = t + j * kGrpThreads;
       active[j] = p < kWinPix;
-      const int hy = p / kHaloPitch, hx = p - hy * kHaloPitch;
+      const int hy = p / kWinPitch, hx = p - hy * kWinPitch;
       off[j] = hy * kBoxW + hx + kBoxX;
     }
-    for (int it = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += 2 * (int)gridDim.x, it += 2) {
+    for (int it = grp, tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += kBuilders * (int)gridDim.x, it += kBuilders) {
       const uint32_t slot = it % kStg;
       mbar_wait(bSFull + 8 * slot, (uint32_t)((it / kStg) & 1));
-      float v[2][CIN];
+      float v[kRecPerThread][CIN];
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < kRecPerThread; ++j)
 #pragma unroll
-        for (int c = 0; c < CIN; ++c) v[j][c] = active[j] ? stg_base[slot * (Stg<CIN>::kSlot / 4) + c * (kHaloRows * kBoxW) + off[j]] : 0.f;
+        for (int c = 0; c < CIN; ++c) v[j][c] = active[j] ? stg_base[slot * (Stg<CIN>::kSlot / 4) + c * (kWinRows * kBoxW) + off[j]] : 0.f;
       // fp16 hi / lo split of the (clamped, denoiser.py:40) input.  The "1" slots are set in every record: they only meet
       // non-zero weights (the bias) in the centre tap, whose pixel is the output pixel itself.
-      uint32_t rec[2][8];
+      uint32_t rec[kRecPerThread][8];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int j = 0; j < kRecPerThread; ++j) {
         __half h16[16];
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) h16[k2] = __float2half_rn(0.f);
@@ -668,7 +672,7 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
       const uint32_t stage = it % kStagesA, use = it / kStagesA;
       mbar_wait(bEmpty + 8 * stage, (use & 1) ^ 1);
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+      for (int j = 0; j < kRecPerThread; ++j)
         if (active[j]) {
           const uint32_t dst = sA + stage * kStageBytes + (uint32_t)(t + j * kGrpThreads) * 16u;
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(rec[j][0]), "r"(rec[j][1]), "r"(rec[j][2]), "r"(rec[j][3]) : "memory");
@@ -678,13 +682,13 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
       mbar_arrive(bFull + 8 * stage);
     }
   } else if (warp == kMmaWarp2 + 1) {
-    // ------------------------------------------------------------ TMA producer: one (16 x 18 x Cin) box per tile
+    // ------------------------------------------------------------ TMA producer: one (136 x 3 x Cin) box per tile
     if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
         const int img = (int)fdiv((uint32_t)tile, div_img), rem = tile - img * per_img;
         const int trow = (int)fdiv((uint32_t)rem, div_tx);
-        const int y0 = trow * kTileRows - 1, x0 = (rem - trow * a.tiles_x) * kTileCols - 1 - kBoxX;
+        const int y0 = trow - 1, x0 = (rem - trow * a.tiles_x) * kTW - 1 - kBoxX;
         const uint32_t slot = it % kStg;
         mbar_wait(bSEmpty + 8 * slot, (uint32_t)(((it / kStg) & 1) ^ 1));
         mbar_expect_tx(bSFull + 8 * slot, Stg<CIN>::kBytes);
@@ -706,8 +710,9 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
       if (elect_one()) {
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-          const uint32_t shift = (uint32_t)((t / 3) * kHaloPitch + (t % 3)) * 16u;
-          umma_f16(d_tmem, desc_k_none(a0 + shift, kChunkPlane, kHaloPitch * 16), desc_k_none(sW + t * kWTap, 64 * 16, 128), kIdescF2,
+          if ((a.dbg & 4) && t >= 3) break;              // timing probe: a third of the MMAs
+          const uint32_t shift = (uint32_t)((t / 3) * kWinPitch + (t % 3)) * 16u;
+          umma_f16(d_tmem, desc_k_none(a0 + shift, kChunkPlane, 128), desc_k_none(sW + t * kWTap, 64 * 16, 128), kIdescF2,
                    t ? 1u : 0u);
         }
         umma_commit(bEmpty + 8 * stage);
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
         uint32_t r0[32];
         tmem_ld32(taddr, r0);
         tmem_ld_wait();
-        stage_half_row1(row_p0, row_p1, lane, r0, 0, a.slope, a.write_a8);
+        if (!(a.dbg & 2)) stage_half_row1(row_p0, row_p1, lane, r0, 0, a.slope, a.write_a8);
       }
       {
         uint32_t r1[32];
@@ -741,20 +746,19 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
-        stage_half_row1(row_p0, row_p1, lane, r1, 1, a.slope, a.write_a8);
+        if (!(a.dbg & 2)) stage_half_row1(row_p0, row_p1, lane, r1, 1, a.slope, a.write_a8);
       }
       __syncwarp();
       if (!(a.dbg & 1)) {
         const int img = (int)fdiv((uint32_t)tile, div_img), rem = tile - img * per_img;
         const int trow = (int)fdiv((uint32_t)rem, div_tx);
-        const int ty0 = trow * kTileRows + q * 4, tx0 = (rem - trow * a.tiles_x) * kTileCols;   // this warp's 4 x 8 piece
-        const bool full = ty0 + 4 <= a.H && tx0 + kTileCols <= a.W;
-        const size_t row_bytes = (size_t)a.W * 128;
-        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out) + ((size_t)img * 2 * hw + (size_t)ty0 * a.W + tx0) * 128;
+        const int tx0 = (rem - trow * a.tiles_x) * kTW + q * 32;          // this warp's 32 pixels of row trow
+        const int left = a.W - tx0;                                       // pixels of the piece inside the image (may be <= 0)
+        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out) + ((size_t)img * 2 * hw + (size_t)trow * a.W + tx0) * 128;
         uint8_t* p1 = p0 + hw * 128;
-        flush_rows<0>(wst, p0 + (lane >> 3) * 128 + (lane & 7) * 16, row_bytes, lane, full, a.H - ty0, a.W - tx0);
-        if (a.write_a8) flush_rows<0>(wst + 4096u, p1 + (lane >> 3) * 128 + (lane & 7) * 16, row_bytes, lane, full, a.H - ty0, a.W - tx0);
-        else flush_rows<4>(wst + 4096u, p1 + (lane >> 2) * 128 + (4 + (lane & 3)) * 16, row_bytes, lane, full, a.H - ty0, a.W - tx0);
+        flush_rows<0>(wst, p0 + (lane >> 3) * 128 + (lane & 7) * 16, lane, left);
+        if (a.write_a8) flush_rows<0>(wst + 4096u, p1 + (lane >> 3) * 128 + (lane & 7) * 16, lane, left);
+        else flush_rows<4>(wst + 4096u, p1 + (lane >> 2) * 128 + (4 + (lane & 3)) * 16, lane, left);
       }
       __syncwarp();                                     // the staging rows are rewritten by the next tile
     }
@@ -1251,7 +1255,7 @@ first2::FastDiv make_fastdiv(uint32_t d) {
   return f;
 }
 
-// fp32 planar network input (nimg, C, H, W) as a 4-D tensor map with a (16 x 18 x C x 1) box, cached per (pointer, planes, C)
+// fp32 planar network input (nimg, C, H, W) as a 4-D tensor map with a (136 x 3 x C x 1) box, cached per (pointer, planes, C)
 const CUtensorMap* plan_input_map(TcPlan* plan, const float* in, int planes, int C) {
   for (auto& e : plan->in_maps)
     if (e.ptr == in && e.planes == planes && e.C == C) return &e.map;
@@ -1263,7 +1267,7 @@ const CUtensorMap* plan_input_map(TcPlan* plan, const float* in, int planes, int
   e.C = C;
   const cuuint64_t dims[4] = {(cuuint64_t)plan->W, (cuuint64_t)plan->H, (cuuint64_t)C, (cuuint64_t)(planes / C)};
   const cuuint64_t strides[3] = {(cuuint64_t)plan->W * 4, (cuuint64_t)plan->H * plan->W * 4, (cuuint64_t)C * plan->H * plan->W * 4};
-  const cuuint32_t box[4] = {(cuuint32_t)first2::kBoxW, (cuuint32_t)kHaloRows, (cuuint32_t)C, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)first2::kBoxW, (cuuint32_t)first2::kWinRows, (cuuint32_t)C, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&e.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1396,10 +1400,14 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
   if (!im2col && (plan->W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (C == 1 || C == 3)) {
     const CUtensorMap* m = plan_input_map(plan, in, nimg * C, C);
     a.dbg = plan->first_dbg;
+    a.tiles_x = (plan->W + first2::kTW - 1) / first2::kTW;      // strips of 128 pixels, one image row per tile
+    a.tiles_y = plan->H;
+    a.ntiles = a.tiles_x * a.tiles_y * nimg;
+    const int grid2 = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
     if (m == nullptr) return cudaErrorInvalidValue;
     const first2::FastDiv di = make_fastdiv((uint32_t)(a.tiles_x * a.tiles_y)), dx = make_fastdiv((uint32_t)a.tiles_x);
-    if (C == 1) first2::conv_first2_kernel<1><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a, di, dx);
-    else first2::conv_first2_kernel<3><<<grid, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a, di, dx);
+    if (C == 1) first2::conv_first2_kernel<1><<<grid2, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a, di, dx);
+    else first2::conv_first2_kernel<3><<<grid2, first2::kThreadsF2, first2::kSmemBytesF2, st>>>(*m, a, di, dx);
     return cudaGetLastError();
   }
   a.w_img = L.w_first_tc;

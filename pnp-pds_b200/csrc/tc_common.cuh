@@ -211,7 +211,8 @@ __device__ __forceinline__ uint32_t e4m3x2_from_f16x2(uint32_t h2) {
 // The first half of plane 1 is a function of plane 0 alone, so a consumer can rebuild it on chip: the row-streaming body
 // kernel does (dncnn_roll.cu), and the layers feeding it skip the store (write_a8 = 0: 192 instead of 256 bytes per pixel).
 __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, const uint32_t (&d0)[32], const uint32_t (&d1)[32],
-                                               const float* bias_s, int c0, float slope, float lo_scale, int write_a8) {
+                                               const float* bias_s, int c0, float slope, float lo_scale, int write_a8, uint32_t cs = 32) {
+  // cs: byte distance between the 32-byte pieces of a row (32; other values only in the store-pattern timing probe of dncnn_roll.cu)
   uint32_t a8[8], l8[8];
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
@@ -231,7 +232,7 @@ __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, 
       l[2 * k] = (v0 - hf.x) * kActLoScale;
       l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
     }
-    st_global_256(dst_p0 + c0 + q * 16, hi);
+    st_global_256(reinterpret_cast<uint8_t*>(dst_p0) + (size_t)(c0 / 16 + q) * cs, hi);
     if (write_a8) {                          // warp-uniform
 #pragma unroll
       for (int k = 0; k < 4; ++k) a8[q * 4 + k] = e4m3x2_from_f16x2(hi[2 * k]) | (e4m3x2_from_f16x2(hi[2 * k + 1]) << 16);
@@ -239,8 +240,8 @@ __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, 
 #pragma unroll
     for (int k = 0; k < 4; ++k) l8[q * 4 + k] = pack_e4m3x4(l[4 * k], l[4 * k + 1], l[4 * k + 2], l[4 * k + 3]);
   }
-  if (write_a8) st_global_256(dst_p1 + c0, a8);
-  st_global_256(dst_p1 + 64 + c0, l8);
+  if (write_a8) st_global_256(dst_p1 + (size_t)(c0 / 32) * cs, a8);
+  st_global_256(dst_p1 + (size_t)(2 + c0 / 32) * cs, l8);
 }
 
 // Programmatic dependent launch: a layer's CTAs may start (barrier init, TMEM alloc, weight loads) while the

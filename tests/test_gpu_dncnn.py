@@ -224,3 +224,32 @@ def test_body_kernels_are_deterministic_run_to_run(shape, variant, name):
         first = e.dncnn_forward(xd).clone()
         for _ in range(11):
             assert bool((e.dncnn_forward(xd) == first).all()), name
+
+
+@pytest.mark.parametrize("shape,arch", [((2, 1, 64, 64), SIMPLE[0]), ((3, 3, 50, 36), SIMPLE[1]), ((1, 1, 23, 128), SIMPLE[0]),
+                                        ((2, 3, 9, 260), SIMPLE[1]), ((1, 1, 40, 132), SIMPLE[0]), ((2, 1, 7, 4), SIMPLE[0]),
+                                        ((1, 3, 33, 321), SIMPLE[1]), ((2, 3, 40, 48), "dncnn_color_blind"), ((1, 1, 48, 48), "dncnn_15")])
+def test_first_layer_kernels_agree(shape, arch):
+    """The tap-shifted first-layer kernel (one K = 16 MMA per tap over 32-byte pixel records, input windows by TMA, bias folded into
+    the centre tap; the default whenever W % 4 == 0) against the im2col kernel (tc_variant bit 15) and the oracle: strips hanging
+    over the right edge (W = 36, 132, 260), images narrower than a strip, one-row bands, W % 4 != 0 (both variants then run the
+    im2col kernel: bit-identical), the KAIR networks (no input clamp, ReLU)."""
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    B, C, H, W = shape
+    w = load_weights(weights_path(arch))
+    x = (np.random.default_rng(31).random(shape).astype(np.float32) * 1.2 - 0.1)     # exercises the input clamp where there is one
+    outs = []
+    for variant in (0, 32768):
+        with Engine(B, C, H, W, conv_engine="tcgen05") as e:
+            e.load_dncnn(w)
+            e.set_tc_variant(variant)
+            outs.append(e.dncnn_forward(e.to_device(x)).cpu().numpy())
+    err = float(np.max(np.abs(outs[0] - outs[1])))
+    print(shape, arch, "tap-shifted vs im2col", err)
+    if W % 4:
+        assert np.array_equal(outs[0], outs[1])
+    assert err < (2e-5 if "dncnn" in arch else 2e-6)        # three fp16 products in both; accumulation order and the bias split differ
+    for b in (0, B - 1):
+        ref = O.dncnn_forward(w.layers, x[b], w.slope, w.residual_sign, w.clamp)
+        assert float(np.max(np.abs(outs[0][b] - ref))) < (1e-4 if "dncnn" in arch else TOL)
