@@ -249,7 +249,10 @@ def test_first_layer_kernels_agree(shape, arch):
     print(shape, arch, "tap-shifted vs im2col", err)
     if W % 4:
         assert np.array_equal(outs[0], outs[1])
-    assert err < (2e-5 if "dncnn" in arch else 2e-6)        # three fp16 products in both; accumulation order and the bias split differ
+    tol = 2e-4 if "dncnn" in arch else TOL      # KAIR networks: no clamps, activations an order of magnitude larger
+    assert err < tol                    # three fp16 products in both; accumulation order and the bias split differ
     for b in (0, B - 1):
         ref = O.dncnn_forward(w.layers, x[b], w.slope, w.residual_sign, w.clamp)
-        assert float(np.max(np.abs(outs[0][b] - ref))) < (1e-4 if "dncnn" in arch else TOL)
+        e_new, e_old = float(np.max(np.abs(outs[0][b] - ref))), float(np.max(np.abs(outs[1][b] - ref)))
+        print("   vs oracle: tap-shifted", e_new, "im2col", e_old)
+        assert e_new < tol and e_old < tol
