@@ -223,6 +223,19 @@ __global__ void __launch_bounds__(256, OX == 8 ? (MODE == kDual ? 4 : 5) : 3) bl
   };
   if constexpr (kEarly) {
     if (live) tail_loads(0);
+  } else if constexpr (MODE == kDual) {
+    // the tail's first-touch operands (t, b, x_true [, s+, s]; x+ and x come through the staging loads) start their way from DRAM
+    // now: one L2 prefetch per operand covers this thread's 64 bytes, and the tail — four outputs at a time — then waits for L2
+    // round trips instead of DRAM ones
+    if (live) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.s.t + g0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.s.obs + g0));
+      if (have_true) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.s.xtrue + g0));
+      if constexpr (METHOD == PDS_METHOD_B) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.s.s_new + g0));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.s.s_old + g0));
+      }
+    }
   }
 
   // stage the halo tile; the periodic wrap is one conditional add / subtract when the image is at least as large as the

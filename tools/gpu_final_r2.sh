@@ -23,10 +23,13 @@ $CMD1 > gpurun_out/plain1.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_cfg1.csv $CMD1 > gpurun_out/ncu_list1.log 2>&1
 echo "rc=$?"; wc -l gpurun_out/launches_cfg1.csv
 echo "== ncu full: conv layers (cfg4 shape)"
-ncu --set full --clock-control none --import-source on -k regex:"conv_roll_d_kernel|conv_first_tc_kernel|conv_last_tc_kernel" -s 60 -c 4 -o gpurun_out/prof_conv_layers -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"conv_roll_d_kernel|conv_first2_kernel|conv_last_tc_kernel" -s 60 -c 4 -o gpurun_out/prof_conv_layers -f $CMD > gpurun_out/ncu_full.log 2>&1
 echo "rc=$?"
 echo "== ncu full: stencils (cfg4 shape)"
-ncu --set full --clock-control none --import-source on -k regex:"blur_rt_kernel" -s 4 -c 2 -o gpurun_out/prof_blur -f $CMD > gpurun_out/ncu_full_blur.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"blur_rt_kernel" -s 10 -c 2 -o gpurun_out/prof_blur -f $CMD > gpurun_out/ncu_full_blur.log 2>&1
+echo "rc=$?"
+echo "== ncu full: im2col first-layer kernel (cross-check, tc_variant bit 15), same shape"
+ncu --set full --clock-control none -k regex:"conv_first_tc_kernel" -s 2 -c 1 -o gpurun_out/prof_first_im2col -f $CMD --tc-variant 32768 > gpurun_out/ncu_full_first_im2col.log 2>&1
 echo "rc=$?"
 echo "== ncu full: chain kernel (cfg1)"
 ncu --set full --clock-control none --import-source on -k regex:"conv_chain_kernel" -s 4 -c 1 -o gpurun_out/prof_chain -f $CMD1 > gpurun_out/ncu_full_chain.log 2>&1
@@ -36,3 +39,4 @@ CMD2="python bench.py --steps 1 --warmup 3 --workload cfg2b --e2e-iters 1 --no-c
 ncu --set full --clock-control none --import-source on -k regex:"dual_pw_kernel|primal_pw_kernel|l1ball_kernel" -s 6 -c 3 -o gpurun_out/prof_pointwise -f $CMD2 > gpurun_out/ncu_full2.log 2>&1
 echo "rc=$?"; ls -la gpurun_out/*.ncu-rep
 python tools/chain_timeline.py 256 256 128 > gpurun_out/timeline_256.txt 2>&1; tail -2 gpurun_out/timeline_256.txt
+python tools/gpu_write_bw.py > gpurun_out/hbm_rw.json 2>&1; cat gpurun_out/hbm_rw.json

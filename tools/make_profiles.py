@@ -135,7 +135,9 @@ def main():
     rep = os.path.join(SRC, "prof_pointwise.ncu-rep")
     if os.path.exists(rep):
         summarize(rep, tag, "ncu_pointwise.json")
-    for name, outn in (("prof_chain", "ncu_chain.json"), ("prof_blur", "ncu_blur.json")):
+    if os.path.exists(os.path.join(SRC, "hbm_rw.json")):
+        shutil.copy(os.path.join(SRC, "hbm_rw.json"), os.path.join(OUT, f"{tag}_hbm_read_write.json"))
+    for name, outn in (("prof_chain", "ncu_chain.json"), ("prof_blur", "ncu_blur.json"), ("prof_first_im2col", "ncu_first_im2col.json")):
         rep = os.path.join(SRC, name + ".ncu-rep")
         if os.path.exists(rep):
             summarize(rep, tag, outn)
@@ -145,9 +147,17 @@ def main():
         if os.path.exists(os.path.join(SRC, name)):
             shutil.copy(os.path.join(SRC, name), os.path.join(OUT, f"{tag}_chain_{name}"))
     # warp-stall samples by warp role (source-line ranges of the kernels' role branches)
-    roles = {"prof_conv_layers": ("dncnn_roll.cu", ROLL_ROLES, "conv_roll_d_kernel", "ncu_roll_roles.json"),
-             "prof_chain": ("dncnn_chain.cu", CHAIN_ROLES, "conv_chain_kernel", "ncu_chain_roles.json")}
-    for name, (src, spec, kern, outn) in roles.items():
+    tc = os.path.join(csrc, "dncnn_tc.cu")
+    first_at = [i + 1 for i, l in enumerate(open(tc).read().splitlines()) if "conv_first2_kernel(const" in l]
+    first_roles = role_spec(tc, [("setup", "conv_first2_kernel(const"), ("record_builders", "// ------------------------------------------------------------ record builders"),
+                                 ("tma_producer", "// ------------------------------------------------------------ TMA producer: one (136"),
+                                 ("mma_issuer", "// ------------------------------------------------------------ MMA issuer: nine"),
+                                 ("epilogue", "// ------------------------------------------------------------ epilogue: four groups"),
+                                 ("teardown", "}  // namespace first2")], after=(first_at[0] - 1 if first_at else 0))
+    roles = [("prof_conv_layers", "dncnn_roll.cu", ROLL_ROLES, "conv_roll_d_kernel", "ncu_roll_roles.json"),
+             ("prof_conv_layers", "dncnn_tc.cu", first_roles, "conv_first2_kernel", "ncu_first_roles.json"),
+             ("prof_chain", "dncnn_chain.cu", CHAIN_ROLES, "conv_chain_kernel", "ncu_chain_roles.json")]
+    for name, src, spec, kern, outn in roles:
         rep = os.path.join(SRC, name + ".ncu-rep")
         if os.path.exists(rep) and spec:
             r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_roles.py"), rep, os.path.join(ROOT, "pnp-pds_b200", "csrc", src), spec, kern],
