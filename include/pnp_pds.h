@@ -200,7 +200,11 @@ int pds_debug_set_conv_engine(pds_handle_t h, int engine);
  * them, bit 8 makes them read the e4m3(a) operand from HBM instead of rebuilding it on chip (every layer then stores it),
  * bit 9 disables the chain kernel (all body layers of a small launch in one persistent launch) in favour of one tile-kernel
  * launch per layer, bits 11 / 12 are timing probes of the chain kernel's MMA issue order (12 gives wrong results by design),
- * bit 13 makes the blur stencils ignore the compile-time tap list of blur_models/blur_1.mat (generic kernels: the cross-check) */
+ * bit 13 makes the blur stencils ignore the compile-time tap list of blur_models/blur_1.mat (generic kernels: the cross-check),
+ * bit 14 runs large stencil launches on 64 x 32 tiles (8 outputs per thread), bit 15 runs the first layer on the im2col kernel
+ * instead of the tap-shifted one (the cross-check), bits 16 - 18 are timing probes of the first layer and of the row-streaming
+ * body kernel's epilogue (no activation stores / no epilogue arithmetic or consecutive-address stores / a third of the first
+ * layer's MMAs: wrong results by design) */
 int pds_debug_set_tc_variant(pds_handle_t h, int variant);
 /* SM-cycle-counter stamps of the chain kernel's pipeline events (dncnn_chain.cu: flags polled, TMA issued, TMEM stage free, first
  * plane landed, MMAs issued, accumulator ready, stored, published) for the first 64 units of CTA 0 of the first 4 clusters:
