@@ -578,7 +578,7 @@ cudaError_t launch_conv_mid_roll(TcPlan* plan, int in_buf, int nimg, int band_ro
   a.in = plan->act[in_buf];
   a.out = plan->act[in_buf ^ 1];
   a.write_a8 = write_a8;
-  a.dbg = plan->first_dbg;
+  a.dbg = plan->probe_bits;
   a.slope = slope;
   a.lo_scale = L.lo_scale;
   a.H = plan->H;

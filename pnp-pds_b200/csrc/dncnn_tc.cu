@@ -237,7 +237,7 @@ struct FirstArgs {
   int clamp_in;
   int write_a8;           // see store_half_row (tc_common.cuh)
   int H, W, nimg, tiles_x, tiles_y, ntiles;
-  int dbg;                // timing probes of the tap-shifted kernel (wrong results): 1 = no activation stores, 2 = no proxy fence
+  int dbg;                // timing probes of the tap-shifted kernel (wrong results): 1 = no activation stores, 2 = no epilogue arithmetic, 4 = a third of the MMAs
 };
 
 template <int CIN>
@@ -1330,7 +1330,7 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   return 0;
 }
 
-void tc_plan_set_first_dbg(TcPlan* p, int bits) { p->first_dbg = bits; }
+void tc_plan_set_probe_bits(TcPlan* p, int bits) { p->probe_bits = bits; }
 
 void tc_plan_destroy(TcPlan* p) {
   if (!p) return;
@@ -1399,7 +1399,7 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
   // other shapes take the im2col kernel
   if (!im2col && (plan->W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (C == 1 || C == 3)) {
     const CUtensorMap* m = plan_input_map(plan, in, nimg * C, C);
-    a.dbg = plan->first_dbg;
+    a.dbg = plan->probe_bits;
     a.tiles_x = (plan->W + first2::kTW - 1) / first2::kTW;      // strips of 128 pixels, one image row per tile
     a.tiles_y = plan->H;
     a.ntiles = a.tiles_x * a.tiles_y * nimg;

@@ -118,7 +118,7 @@ cudaError_t launch_conv_last(int nimg, int C, int H, int W, const __half* act_in
 struct TcPlan;  // opaque: tensor maps for the two activation buffers
 int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** out);  // returns 0 / error (message set)
 void tc_plan_destroy(TcPlan* p);
-void tc_plan_set_first_dbg(TcPlan* p, int bits);
+void tc_plan_set_probe_bits(TcPlan* p, int bits);
 // in_buf: 0 or 1 (which activation buffer is the input; the other is the output)
 cudaError_t launch_conv_mid_tc(TcPlan* plan, int in_buf, int nimg, const DncnnLayerW& L, float slope, cudaStream_t st);
 // write_a8: also store the e4m3(fp16(v)) half of plane 1 (0 when the next layer is the row-streaming kernel, which rebuilds it)

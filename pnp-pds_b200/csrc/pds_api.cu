@@ -238,7 +238,7 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const bool two_cta = bd.two_cta;
     const bool derive = band > 0 && !(h->tc_variant & 256);
     if (h->conv_engine == PDS_CONV_TCGEN05) {
-      tc_plan_set_first_dbg(h->tc, (h->tc_variant >> 16) & 7);   // bits 16 / 17: timing probes of the first layer (wrong results)
+      tc_plan_set_probe_bits(h->tc, (h->tc_variant >> 16) & 7);   // bits 16 - 18: timing probes (wrong results by design, include/pnp_pds.h)
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first_tc(h->tc, nimg, d.C, cin, h->layers[0], h->slope, h->clamp, derive ? 0 : 1, (h->tc_variant & 32768) ? 1 : 0, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_FIRST, st, launch_conv_first(nimg, d.C, d.H, d.W, cin, h->layers[0], h->slope, h->clamp, h->act[0], st));

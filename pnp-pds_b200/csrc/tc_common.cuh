@@ -38,7 +38,7 @@ struct TcPlan {
   // first layer (tap-shifted kernel): tensor maps over the fp32 network input, one per (pointer, planes) seen
   struct InMap { const float* ptr; int planes, C; CUtensorMap map; };
   std::vector<InMap> in_maps;
-  int first_dbg = 0;                    // timing probes of the first layer (tc_variant bits 16 / 17, wrong results by design)
+  int probe_bits = 0;                   // timing probes of the first layer and of the row-streaming epilogue (tc_variant bits 16 - 18, wrong results by design)
 };
 int chain_setup();
 int tc_plan_set_chain(TcPlan* plan, const std::vector<ChainLayer>& layers);
