@@ -777,34 +777,47 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
 // shared memory nine times.  Instead the contraction over the 64 input channels is done ONCE per halo pixel for all
 // nine taps at the same time:
 //     P[q][tap*C + c] = sum_ci act[q][ci] * W[c][tap][ci]          q over the 18x10 halo tile,  N = 9*C <= 27 -> 32 columns
-// as two M=128 MMA blocks over the contiguous halo tile (rows 0..127 and rows 52..179), and the epilogue gathers
+// as two M=128 MMA blocks over the contiguous halo tile (halo pixels 0..127 and 56..183: both 1024-byte aligned; the rows past
+// pixel 179 are never gathered), and the epilogue gathers
 //     out[y][x][c] = sum_tap P[(y+dy)*10 + (x+dx)][tap*C + c]  + bias, residual, clamp
-// through a shared-memory copy of P.  16 MMAs per tile instead of 72; the kernel is bound by streaming the activations.
-// Operand split as in the body layers: plane 0 x fp16 w_hi (kind::f16) + plane 1 x e4m3 [w_lo 2^S | w_hi 2^(S-10)] (kind::f8f6f4).
+// through a shared-memory copy of P.  The kernel is bound by streaming the activations, so it reads as few of them as the
+// operand split allows: the fp16 plane (128 B per pixel) and the a_lo half of plane 1 (64 B per pixel, its own SWIZZLE_64B
+// tensor map and K-major descriptors) — not e4m3(fp16(a)), which the body layers use for their a*w_lo correction.  With almost no
+// tensor work here, that correction runs in fp16 on the plane that is loaded anyway:
+//     kind::f16,    K = 64:  a_hi x [ w_hi ; w_lo 2^S ]          N = 64: columns 0-31 the product, 32-63 the first correction
+//     kind::f8f6f4, K = 64:  e4m3(a_lo 2^10) x e4m3(w_hi 2^(S-10))   N = 32: the second correction, same scale 2^S
+// So no body layer stores e4m3(fp16(a)) for this kernel's sake (192 instead of 256 bytes per pixel read here).
 // ---------------------------------------------------------------------------------------------
 namespace last {
-constexpr int kSlotsL = 6;
+constexpr int kSlotsL = 4;                                // tile slots: fp16 plane box + a_lo half box
 constexpr int kThreadsL = 64 + 2 * 128;                   // TMA warp, MMA warp, two epilogue groups of four warps
 constexpr int kNL = 32;                                   // B rows (tap*C + c), zero beyond 9*C
-constexpr uint32_t kWTileL = kNL * 128, kWBytesL = 2 * kWTileL;   // fp16 tile + e4m3 tile
+constexpr uint32_t kW16 = 2 * kNL * 128, kW8 = kNL * 64, kWBytesL = kW16 + kW8;   // fp16 tile [w_hi ; w_lo 2^S] (SW128) + e4m3 tile (SW64)
 constexpr int kHaloPix = kHaloRows * kHaloPitch;          // 180
-constexpr int kBlk1 = kHaloPix - 128;                     // second MMA block starts at halo pixel 52
+constexpr int kBlk1 = 56;                                 // second MMA block starts at halo pixel 56
+constexpr uint32_t kLoBytes = kHaloPix * 64;              // 11520 bytes landed by the a_lo box
+constexpr uint32_t kLoSlot = 12 * 1024;
+constexpr uint32_t kTileSlot = kPlaneSlot + kLoSlot;      // 35 KB
+constexpr int kPRows = kBlk1 + 128;                       // P rows written (184; rows >= 180 are dead)
 constexpr int kPStride = 29;                              // floats per halo pixel in the P copy (odd: conflict-free rows)
-constexpr uint32_t kOffAL = kWBytesL, kOffBarL = kOffAL + kSlotsL * kPlaneSlot;
+constexpr uint32_t kOffAL = 11 * 1024, kOffBarL = kOffAL + kSlotsL * kTileSlot;
 constexpr uint32_t kOffBiasL = kOffBarL + 192, kOffPL = kOffBiasL + 64;
-constexpr uint32_t kSmemBytesL = kOffPL + 2 * kHaloPix * kPStride * 4 + 1024;
-constexpr uint32_t kIdescL = kIdescBase | ((uint32_t)(kNL >> 3) << 17);
+constexpr uint32_t kSmemBytesL = kOffPL + 2 * kPRows * kPStride * 4 + 1024;
+constexpr uint32_t kIdescL16 = kIdescBase | ((uint32_t)(2 * kNL >> 3) << 17), kIdescL8 = kIdescBase | ((uint32_t)(kNL >> 3) << 17);
+constexpr uint32_t kAccCols = 192;                        // per TMEM stage: [block 0: 64 | block 1: 64 | f8 block 0: 32 | f8 block 1: 32]
+static_assert(kWBytesL <= kOffAL && kPlaneBytes + (kPRows - kHaloPix) * 128 <= kPlaneSlot && kPRows * 64 <= kLoSlot, "slot slack");
 
 template <int C>
-__global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcArgs a) {
+__global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_lo,
+                                                                    TcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - raw);
   const uint32_t sW = base, sA = base + kOffAL, sBar = base + kOffBarL;
-  // barriers: full[6] @0, empty[6] @48, wfull @96, tfull[2] @104, tempty[2] @120, tmem slot @136
-  const uint32_t bFull = sBar, bEmpty = sBar + 48, bW = sBar + 96, bTFull = sBar + 104, bTEmpty = sBar + 120;
-  const uint32_t sTmemSlot = sBar + 136;
+  // barriers: full[4] @0, empty[4] @32, wfull @64, tfull[2] @72, tempty[2] @88, tmem slot @104
+  const uint32_t bFull = sBar, bEmpty = sBar + 32, bW = sBar + 64, bTFull = sBar + 72, bTEmpty = sBar + 88;
+  const uint32_t sTmemSlot = sBar + 104;
   float* bias_s = reinterpret_cast<float*>(gbase + kOffBiasL);
   float* P = reinterpret_cast<float*>(gbase + kOffPL);
 
@@ -819,21 +832,22 @@ __global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid
     mbar_init(bTEmpty, 4); mbar_init(bTEmpty + 8, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_lo) : "memory");
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + C) bias_s[threadIdx.x - 64] = a.bias[threadIdx.x - 64];
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sTmemSlot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarL + 136);
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(gbase + kOffBarL + 104);
   pdl_launch_dependents();
 
   const int per_img = a.tiles_x * a.tiles_y;
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------ TMA producer: two boxes per tile on one barrier
     if (elect_one()) {
       mbar_expect_tx(bW, kWBytesL);
       bulk_load(sW, a.w_img, kWBytesL, bW);
@@ -841,58 +855,54 @@ __global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid
     __syncwarp();
     pdl_wait_prior_grid();
     uint32_t j = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
       const int img = tile / per_img, rem = tile - img * per_img;
       const int y0 = (rem / a.tiles_x) * kTileRows, x0 = (rem % a.tiles_x) * kTileCols;
-#pragma unroll
-      for (int p = 0; p < 2; ++p, ++j) {
-        const uint32_t slot = j % kSlotsL, use = j / kSlotsL;
-        mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(bFull + 8 * slot, kPlaneBytes);
-          tma_load_4d(sA + slot * kPlaneSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2 + p);
-        }
-        __syncwarp();
+      const uint32_t slot = j % kSlotsL, use = j / kSlotsL;
+      mbar_wait(bEmpty + 8 * slot, (use & 1) ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(bFull + 8 * slot, kPlaneBytes + kLoBytes);
+        tma_load_4d(sA + slot * kTileSlot, &tmap, bFull + 8 * slot, 0, x0 - 1, y0 - 1, img * 2);
+        tma_load_4d(sA + slot * kTileSlot + kPlaneSlot, &tmap_lo, bFull + 8 * slot, 32, x0 - 1, y0 - 1, img * 2 + 1);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer: 2 planes x 2 row blocks x 4 k-steps
+    // ------------------------------------------------------------ MMA issuer: 2 row blocks x (4 fp16 + 2 e4m3 k-steps)
     mbar_wait(bW, 0);
-    const uint32_t w_lo = ((sW & 0x3FFFFu) >> 4) | (1u << 16);
-    constexpr uint32_t kHi = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO = 8 contiguous 128-byte rows, SWIZZLE_128B
+    const uint32_t w16 = ((sW & 0x3FFFFu) >> 4) | (1u << 16), w8 = (((sW + kW16) & 0x3FFFFu) >> 4) | (1u << 16);
+    constexpr uint32_t kHi128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO = 8 contiguous 128-byte rows, SWIZZLE_128B
+    constexpr uint32_t kHi64 = (512u >> 4) | (1u << 14) | (4u << 29);       // SBO = 8 contiguous 64-byte rows, SWIZZLE_64B
     uint32_t j = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1;
-      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
-      const uint32_t d_tmem = tmem_base + acc * 128u;
+    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++j) {
+      const uint32_t acc = j & 1, slot = j % kSlotsL, use = j / kSlotsL;
+      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((j >> 1) & 1) ^ 1));
+      mbar_wait(bFull + 8 * slot, use & 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      const uint32_t a16 = (((sA + slot * kTileSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a8 = (((sA + slot * kTileSlot + kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
+      if (elect_one()) {
 #pragma unroll
-      for (int p = 0; p < 2; ++p, ++j) {
-        const uint32_t slot = j % kSlotsL, use = j / kSlotsL;
-        mbar_wait(bFull + 8 * slot, use & 1);
-        tc_fence_after();
-        const uint32_t a_lo = (((sA + slot * kPlaneSlot) & 0x3FFFFu) >> 4) | (1u << 16);
-        if (elect_one()) {
+        for (int b = 0; b < 2; ++b) {
 #pragma unroll
-          for (int b = 0; b < 2; ++b)
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem + (uint32_t)(b * 64), desc64(a16 + ((uint32_t)(b * kBlk1 * 128 + k * 32) >> 4), kHi128), desc64(w16 + ((uint32_t)(k * 32) >> 4), kHi128),
+                     kIdescL16, k ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t ao = (uint32_t)(b * kBlk1 * 128 + k * 32) >> 4;
-              const uint32_t bo = (uint32_t)(p * (int)kWTileL + k * 32) >> 4;
-              const uint32_t d = d_tmem + (uint32_t)(p * 64 + b * 32);
-              if (p == 0) umma_f16(d, desc64(a_lo + ao, kHi), desc64(w_lo + bo, kHi), kIdescL, k ? 1u : 0u);
-              else umma_f8(d, desc64(a_lo + ao, kHi), desc64(w_lo + bo, kHi), kIdescL, k ? 1u : 0u);
-            }
-          umma_commit(bEmpty + 8 * slot);
-          if (p == 1) umma_commit(bTFull + 8 * acc);
+          for (int k = 0; k < 2; ++k)
+            umma_f8(d_tmem + (uint32_t)(128 + b * 32), desc64(a8 + ((uint32_t)(b * kBlk1 * 64 + k * 32) >> 4), kHi64), desc64(w8 + ((uint32_t)(k * 32) >> 4), kHi64),
+                    kIdescL8, k ? 1u : 0u);
         }
-        __syncwarp();
+        umma_commit(bEmpty + 8 * slot);
+        umma_commit(bTFull + 8 * acc);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------ epilogue: TMEM -> P (shared) -> 3x3 gather -> planar fp32.
     // Two groups of four warps: a tile's epilogue is one dependent chain per thread (TMEM read, P write, barrier, gather, store)
-    // and this layer has only 16 MMAs per tile to hide it behind; group g drains the tiles with it % 2 == g, i.e. accumulator
+    // and this layer has only 12 MMAs per tile to hide it behind; group g drains the tiles with it % 2 == g, i.e. accumulator
     // stage g, through its own P buffer and named barrier.
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
@@ -912,28 +922,41 @@ __global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid
       for (int c = 0; c < C; ++c) xin[c] = live ? __ldg(a.net_in + ((size_t)img * C + c) * hw + pix) : 0.f;
       mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128u;
-      float* Pb = P + grp * (kHaloPix * kPStride);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kAccCols;
+      float* Pb = P + grp * (kPRows * kPStride);
+      float p0[9 * C], p1[9 * C];
       {
-        uint32_t r0[32], r1[32], r2[32], r3[32];
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 64, r2);
-        tmem_ld32(taddr + 32, r1);
-        tmem_ld32(taddr + 96, r3);
+        uint32_t r0[32], r1[32], r2[32];
+        tmem_ld32(taddr, r0);                    // block 0: a_hi w_hi
+        tmem_ld32(taddr + 32, r1);               //          a_hi (w_lo 2^S)
+        tmem_ld32(taddr + 128, r2);              //          (a_lo 2^10) (w_hi 2^(S-10))
+        tmem_ld_wait();
+#pragma unroll
+        for (int n = 0; n < 9 * C; ++n) p0[n] = fmaf(__uint_as_float(r1[n]) + __uint_as_float(r2[n]), a.lo_scale, __uint_as_float(r0[n]));
+      }
+      {
+        uint32_t r0[32], r1[32], r2[32];
+        tmem_ld32(taddr + 64, r0);               // block 1
+        tmem_ld32(taddr + 96, r1);
+        tmem_ld32(taddr + 160, r2);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_relaxed(bTEmpty + 8 * acc);
-        // the group's previous tile has been gathered out of Pb by all four warps
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
+#pragma unroll
+        for (int n = 0; n < 9 * C; ++n) p1[n] = fmaf(__uint_as_float(r1[n]) + __uint_as_float(r2[n]), a.lo_scale, __uint_as_float(r0[n]));
+      }
+      // the group's previous tile has been gathered out of Pb by all four warps
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+      {
         float* row0 = Pb + t * kPStride;                   // halo pixel t            (block 0)
 #pragma unroll
-        for (int n = 0; n < 9 * C; ++n) row0[n] = fmaf(__uint_as_float(r2[n]), a.lo_scale, __uint_as_float(r0[n]));
-        if (t >= 128 - kBlk1) {                            // halo pixel 52 + t >= 128 (block 1; the rest duplicates block 0)
+        for (int n = 0; n < 9 * C; ++n) row0[n] = p0[n];
+        if (t >= 128 - kBlk1 && kBlk1 + t < kHaloPix) {    // halo pixel 56 + t >= 128 (block 1; the rest duplicates block 0 or is dead)
           float* row1 = Pb + (kBlk1 + t) * kPStride;
 #pragma unroll
-          for (int n = 0; n < 9 * C; ++n) row1[n] = fmaf(__uint_as_float(r3[n]), a.lo_scale, __uint_as_float(r1[n]));
+          for (int n = 0; n < 9 * C; ++n) row1[n] = p1[n];
         }
       }
       if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // P of this tile complete
@@ -966,7 +989,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) conv_last_tc_kernel(const __grid
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 }  // namespace last
@@ -1231,15 +1254,18 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W, int box_w, int box_h) {
+// box_c = 64: whole 128-byte pixel rows (SWIZZLE_128B); box_c = 32: half rows (the last layer's a_lo box, SWIZZLE_64B)
+int make_act_map(CUtensorMap* map, __half* act, int nimg, int H, int W, int box_w, int box_h, int box_c = 64) {
   EncodeTiledFn enc = get_encode();
   PDS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nimg * 2};
   const cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
-  const cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, act, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   box_c == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   box_c == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,     // half rows: no promotion to whole lines
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PDS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
   return 0;
 }
@@ -1299,6 +1325,8 @@ int tc_plan_create(int nimg, int H, int W, __half* act0, __half* act1, TcPlan** 
   if (!rc) rc = make_act_map(&p->map[1], act1, nimg, H, W, kHaloPitch, kHaloRows);
   if (!rc) rc = make_act_map(&p->map_row[0], act0, nimg, H, W, 130, 1);      // dncnn_roll.cu: 128-pixel strip + x halo
   if (!rc) rc = make_act_map(&p->map_row[1], act1, nimg, H, W, 130, 1);
+  if (!rc) rc = make_act_map(&p->map_lo[0], act0, nimg, H, W, kHaloPitch, kHaloRows, 32);    // last layer: a_lo half of plane 1
+  if (!rc) rc = make_act_map(&p->map_lo[1], act1, nimg, H, W, kHaloPitch, kHaloRows, 32);
   if (!rc) rc = roll_setup();
   if (!rc) rc = chain_setup();
   if (!rc) {
@@ -1430,8 +1458,8 @@ cudaError_t launch_conv_last_tc(TcPlan* plan, int in_buf, int nimg, int C, const
   a.lo_scale = L.lo_scale;
   fill_common(a, plan, nimg);
   const int grid = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
-  if (C == 1) return launch_pdl(last::conv_last_tc_kernel<1>, grid, last::kThreadsL, last::kSmemBytesL, st, plan->map[in_buf], a);
-  if (C == 3) return launch_pdl(last::conv_last_tc_kernel<3>, grid, last::kThreadsL, last::kSmemBytesL, st, plan->map[in_buf], a);
+  if (C == 1) return launch_pdl(last::conv_last_tc_kernel<1>, grid, last::kThreadsL, last::kSmemBytesL, st, plan->map[in_buf], plan->map_lo[in_buf], a);
+  if (C == 3) return launch_pdl(last::conv_last_tc_kernel<3>, grid, last::kThreadsL, last::kSmemBytesL, st, plan->map[in_buf], plan->map_lo[in_buf], a);
   return cudaErrorInvalidValue;
 }
 

@@ -103,7 +103,8 @@ struct DncnnLayerW {
   const __half* w_mid_tc; // smem image for the tcgen05 engine: [9 taps][fp16 tile | e4m3 tile][64 oc][128 B], 128B-swizzled rows
   const __half* w_mid_tc2; // 2-CTA engine: [cta 2][tap 9][fp16 tile 32 rows | e4m3 tile 32 rows][128 B], swizzled
   const float* w_last;    // [Cout][9][64 ci]                            last layer (SIMT engine)
-  const __half* w_last_tc; // [fp16 tile | e4m3 tile][32 rows n = tap*Cout + c][128 B] swizzled, rows >= 9*Cout zero   last layer (tcgen05 engine)
+  const __half* w_last_tc; // last layer (tcgen05 engine): fp16 tile [w_hi 32 rows ; w_lo 2^S 32 rows] x 128 B (SWIZZLE_128B), then e4m3 tile
+                           // [w_hi 2^(S-10)] 32 rows x 64 B (SWIZZLE_64B); row n = tap*Cout + c, rows >= 9*Cout zero
   float lo_scale;         // 2^-S of the e4m3 correction accumulator (tcgen05 engine, pds_api.cu tc_split_scales)
   const float* bias;      // [Cout of this layer]
 };

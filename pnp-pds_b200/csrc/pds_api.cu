@@ -253,8 +253,9 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     }
     for (int l = 1; l < h->depth - 1 && !chain; ++l) {
       if (h->conv_engine == PDS_CONV_TCGEN05 && band > 0) {
-        // the last layer reads the full plane 1 through TMA, so the body layer feeding it stores e4m3(a)
-        const int write_a8 = (!derive || l == h->depth - 2) ? 1 : 0;
+        // e4m3(fp16(a)) is stored only for consumers that read it from HBM (the last layer does not: it takes the fp16 plane and
+        // the a_lo half of plane 1)
+        const int write_a8 = derive ? 0 : 1;
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_roll(h->tc, src, nimg, band, h->layers[l], h->slope, derive ? 1 : 0, write_a8, st));
       } else if (h->conv_engine == PDS_CONV_TCGEN05 && two_cta) {
         PDS_LAUNCH_P(h, PDS_PROF_CONV_MID, st, launch_conv_mid_tc2(h->tc, src, nimg, h->layers[l], h->slope, st));
@@ -841,15 +842,26 @@ int pds_load_dncnn(pds_handle_t h, const void* blob, size_t nbytes) {
       PDS_TRY(dev_alloc(h, &dw, buf.size()));
       PDS_CUDA_OK(cudaMemcpy(dw, buf.data(), buf.size() * 4, cudaMemcpyHostToDevice));
       L.w_last = dw;
-      // tcgen05 engine: [fp16 tile | e4m3 tile][32 rows][128 B]; B row n = tap*Cout + c holds W[c][tap][ci 0..63]
-      // (all nine taps side by side along N, dncnn_tc.cu namespace last), rows >= 9*Cout are zero, 128B-swizzled rows
+      // tcgen05 engine (dncnn_tc.cu namespace last): B row n = tap*Cout + c holds W[c][tap][ci 0..63], all nine taps side by side
+      // along N, rows >= 9*Cout zero.  fp16 tile: 64 rows x 128 B, rows 0-31 w_hi[n], rows 32-63 (w_lo 2^S)[n], 16-byte chunk j of
+      // row r at j ^ (r & 7) (SWIZZLE_128B); then the e4m3 tile: 32 rows x 64 B of e4m3(w_hi 2^(S-10))[n], chunk j at
+      // j ^ ((r >> 1) & 3) (SWIZZLE_64B)
       const TcSplit sp = tc_split_scales(w, (size_t)co * ci * 9);
       L.lo_scale = sp.lo_scale;
-      std::vector<__half> img((size_t)2 * 32 * 64, __float2half_rn(0.f));
+      std::vector<__half> img((size_t)64 * 64 + 32 * 32, __float2half_rn(0.f));
+      uint8_t* img8 = reinterpret_cast<uint8_t*>(img.data() + (size_t)64 * 64);
       for (int tp = 0; tp < 9; ++tp)
         for (int o = 0; o < co; ++o)
-          for (int c = 0; c < 64; ++c)
-            tc_put_weight(img.data(), img.data() + (size_t)32 * 64, tp * co + o, c, w[((size_t)o * ci + c) * 9 + tp], sp);
+          for (int c = 0; c < 64; ++c) {
+            const int n = tp * co + o;
+            const float v = w[((size_t)o * ci + c) * 9 + tp];
+            const __half hi = __float2half_rn(v);
+            const float lo = v - __half2float(hi);
+            img[(size_t)n * 64 + (((c >> 3) ^ (n & 7)) << 3) + (c & 7)] = hi;
+            img[(size_t)(32 + n) * 64 + (((c >> 3) ^ ((32 + n) & 7)) << 3) + (c & 7)] = __float2half_rn(lo * sp.s_lo);
+            img8[(size_t)n * 64 + (((c >> 4) ^ ((n >> 1) & 3)) << 4) + (c & 15)] =
+                (uint8_t)__nv_cvt_float_to_fp8(__half2float(hi) * sp.s_hi, __NV_SATFINITE, __NV_E4M3);
+          }
       __half* dh = nullptr;
       PDS_TRY(dev_alloc(h, &dh, img.size()));
       PDS_CUDA_OK(cudaMemcpy(dh, img.data(), img.size() * sizeof(__half), cudaMemcpyHostToDevice));

@@ -25,6 +25,7 @@ constexpr int kChainMaxPairs = 16384;   // launches of up to 2 Mpx can run as on
 struct TcPlan {
   CUtensorMap map[2];       // halo-tile boxes (64 ch x 10 px x 18 rows) for the 16x8-pixel tile kernels
   CUtensorMap map_row[2];   // row boxes (64 ch x 130 px x 1 row) for the row-streaming body kernel
+  CUtensorMap map_lo[2];    // halo-tile boxes over the a_lo half of plane 1 (32 halves x 10 px x 18 rows, SWIZZLE_64B): last layer
   __half* act[2];
   int nimg, H, W;
   int num_sms;
