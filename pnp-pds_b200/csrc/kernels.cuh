@@ -67,7 +67,6 @@ struct BlurTaps {            // device arrays, built by pds_set_blur_kernel
   int ntaps;
   int ry, rx;                // max |dy|, max |dx|
   int debug_generic;         // test hook: 1 = never use the compile-time tap list of blur_1.mat (the generic kernels are the cross-check)
-  int debug_no_stream;       // test hook: 1 = large launches stay on the tile-per-block stencil (the cross-check of the streaming kernel)
   int debug_ox;              // test hook: outputs per thread of the register-tiled stencil for large launches (0 = default)
   const float* w_host;       // host copies (owned by the handle): the register-tiled stencil takes the weight box by value
   const short2* off_host[2];

@@ -1157,8 +1157,7 @@ int pds_debug_set_tc_variant(pds_handle_t h, int variant) {
   if (!h) return 1;
   h->tc_variant = variant;
   h->taps.debug_generic = (variant & 8192) ? 1 : 0;
-  h->taps.debug_ox = (variant & 16384) ? 8 : 0;
-  h->taps.debug_no_stream = (variant & 524288) ? 1 : 0;  // bit 19: no streaming stencil kernel          // bit 14: 64 x 32 stencil tiles (8 outputs per thread) for large launches     // bit 13: generic blur stencils instead of blur_1.mat's compile-time tap list
+  h->taps.debug_ox = (variant & 16384) ? 8 : 0;          // bit 14: 64 x 32 stencil tiles (8 outputs per thread) for large launches     // bit 13: generic blur stencils instead of blur_1.mat's compile-time tap list
   return 0;
 }
 

@@ -382,254 +382,6 @@ __global__ void __launch_bounds__(256, OX == 8 ? (MODE == kDual ? 4 : 5) : 3) bl
   }
 }
 
-inline int blur_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-    n = v;
-  }
-  return n;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Streaming variant of the fused primal / dual stencils for launches that fill the GPU (blur_1.mat's box, W % 4 == 0): one
-// persistent block per SM walks a contiguous range of 128 x 32 tiles and no thread ever waits for a global load it issued —
-// the halo of tile i+1 (x+ and x, or t) and the tail operands of tile i (t, b, x_true, or x) are on their way through cp.async
-// while tile i's 109 FMAs per output run.  ncu on blur_rt_kernel (cfg4 shape): 16-20 % of the dual kernel's stall samples were in
-// the FMA loop, the rest waited for the staging loads (two dependent streams), the tail's five DRAM reads per output and the
-// barriers behind them, whatever the occupancy.  Same tile geometry, thread mapping, FMA order and tail arithmetic as
-// blur_rt_kernel<.., 8, 4, 16, SPEC>: bit-identical results (the block-level partial sums are added to the trace row in a
-// different order).
-//   shared memory: raw halo tiles [2 stages][x+ | x] (dual) or [2 stages][t] (primal), pitch 164 floats like the compute tile;
-//                  dual only: the combined tile 2x+ - x;  tail operands of the current tile, each thread's own 16 outputs.
-template <int MODE, int METHOD, int SPEC>
-__global__ void __launch_bounds__(256, MODE == kPrimal ? 2 : 1) blur_stream_kernel(const __grid_constant__ BlurArgs a, int ntiles, int tiles_y) {
-  constexpr int RY = 8, RX = 4, OX = 16, TWR = 128, THR = 32;
-  constexpr int HC = TWR + 2 * RX, HR = THR + 2 * RY, PITCH = ((HC + 27) / 32) * 32 + 4, HC4 = HC / 4, NQ = HR * HC4;
-  constexpr int NV = OX + 2 * RX, NV4 = (NV + 3) / 4;
-  constexpr int kTile = HR * PITCH;                          // floats per halo tile
-  constexpr int NRAW = MODE == kDual ? 2 : 1;                // raw arrays per stage
-  constexpr int NOPS = MODE == kDual ? 3 : 1;                // tail operands (t, b, x_true | x)
-  extern __shared__ __align__(16) float smem[];
-  float* raw = smem;                                         // [2][NRAW][kTile]
-  float* comb = raw + 2 * NRAW * kTile;                      // dual: 2x+ - x
-  float* ops = comb + (MODE == kDual ? kTile : 0);           // [NOPS][256 threads][16]
-  __shared__ double red[NACC * 8];
-  __shared__ float sg_s;
-  const Dims d = a.s.d;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_plane = a.tiles_x * tiles_y;
-  const int t_begin = (int)(((long long)ntiles * blockIdx.x) / gridDim.x), t_end = (int)(((long long)ntiles * (blockIdx.x + 1)) / gridDim.x);
-  const bool have_true = MODE == kDual && a.s.xtrue != nullptr;
-
-  auto tile_geo = [&](int tile, int& plane, int& y0, int& x0) {
-    plane = tile / per_plane;
-    const int rem = tile - plane * per_plane;
-    const int tyi = rem / a.tiles_x;
-    y0 = tyi * THR;
-    x0 = (rem - tyi * a.tiles_x) * TWR;
-  };
-  auto cp16 = [](float* dst, const float* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-  };
-  // halo of a tile -> raw stage (periodic wrap per 16-byte chunk: W % 4 == 0 and the image is at least as large as the reach)
-  auto issue_halo = [&](int tile, int stage) {
-    int plane, y0, x0;
-    tile_geo(tile, plane, y0, x0);
-    const size_t pbase = (size_t)plane * d.hw;
-    float* dst = raw + (size_t)stage * NRAW * kTile;
-    for (int i = threadIdx.x; i < NQ; i += 256) {
-      const int hy = i / HC4, q = i - hy * HC4;
-      int gy = y0 - RY + hy, gx = x0 - RX + 4 * q;
-      gy += gy < 0 ? d.H : 0; gy -= gy >= d.H ? d.H : 0;
-      gx += gx < 0 ? d.W : 0; gx -= gx >= d.W ? d.W : 0;
-      const size_t g = pbase + (size_t)gy * d.W + gx;
-      float* p = dst + hy * PITCH + 4 * q;
-      if constexpr (MODE == kPrimal) cp16(p, a.s.t + g);
-      else {
-        cp16(p, a.s.xn + g);
-        cp16(p + kTile, a.s.x + g);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  // this thread's own tail operands (its 16 outputs of the tile) -> ops
-  float* my_ops = ops + threadIdx.x * 16;
-  auto issue_ops = [&](int tile) {
-    int plane, y0, x0;
-    tile_geo(tile, plane, y0, x0);
-    const int gy = y0 + lane, gx0 = x0 + OX * warp;
-    if (gy < d.H) {
-      const size_t g0 = (size_t)plane * d.hw + (size_t)gy * d.W + gx0;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (gx0 + 4 * q >= d.W) break;
-        if constexpr (MODE == kPrimal) cp16(my_ops + 4 * q, a.s.x + g0 + 4 * q);
-        else {
-          cp16(my_ops + 4 * q, a.s.t + g0 + 4 * q);
-          cp16(my_ops + 4096 + 4 * q, a.s.obs + g0 + 4 * q);
-          if (have_true) cp16(my_ops + 8192 + 4 * q, a.s.xtrue + g0 + 4 * q);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  float acc_t = 0.f, acc_dx = 0.f, acc_x = 0.f, acc_e = 0.f;
-  int cur_b = -1;
-  ItemParams p{};
-  float sg = 1.f, la = 0.f, lg4 = 0.f;
-  auto flush_sums = [&]() {
-    if constexpr (MODE == kDual) {
-      double v[NACC] = {(double)acc_t, (double)acc_dx, (double)acc_x, (double)acc_e};
-      block_accumulate<NACC>(v, a.s.sums_cur + (size_t)cur_b * NSUM, red);
-      acc_t = acc_dx = acc_x = acc_e = 0.f;
-    }
-  };
-
-  if (t_begin < t_end) {
-    issue_halo(t_begin, 0);
-    issue_ops(t_begin);
-  }
-  for (int tile = t_begin, it = 0; tile < t_end; ++tile, ++it) {
-    int plane, y0, x0;
-    tile_geo(tile, plane, y0, x0);
-    const int b = plane / d.C;
-    if (b != cur_b) {                                        // block-uniform
-      if (cur_b >= 0) flush_sums();
-      cur_b = b;
-      if (threadIdx.x == 0) sg_s = item_sigma(METHOD, a.s.sums_prev, b, a.s.prm[b]);
-    }
-    // groups in flight, oldest first: halo(tile), ops(tile)  ->  the halo has landed when at most one group is pending
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();                                         // halo(tile) of every thread visible; tail(tile - 1) finished everywhere
-    p = a.s.prm[b];
-    sg = sg_s;
-    la = p.lam * p.alpha;
-    lg4 = 4.f * p.lam * p.g2;
-    const int stage = it & 1;
-    const float* rs = raw + (size_t)stage * NRAW * kTile;
-    const float* tilep = rs;
-    if constexpr (MODE == kDual) {
-      for (int i = threadIdx.x; i < NQ; i += 256) {
-        const int hy = i / HC4, q = i - hy * HC4;
-        const float4 xn4 = *reinterpret_cast<const float4*>(rs + hy * PITCH + 4 * q);
-        const float4 x4 = *reinterpret_cast<const float4*>(rs + kTile + hy * PITCH + 4 * q);
-        float4 v;
-        v.x = 2.f * xn4.x - x4.x; v.y = 2.f * xn4.y - x4.y;
-        v.z = 2.f * xn4.z - x4.z; v.w = 2.f * xn4.w - x4.w;
-        *reinterpret_cast<float4*>(comb + hy * PITCH + 4 * q) = v;
-      }
-      __syncthreads();
-      tilep = comb;
-    }
-    if (tile + 1 < t_end) issue_halo(tile + 1, stage ^ 1);   // the other stage was last read by tail(tile - 1)
-    else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count uniform
-
-    float acc[OX];
-#pragma unroll
-    for (int c = 0; c < OX; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int dyi = 0; dyi < 2 * RY + 1; ++dyi) {
-      const float4* rp = reinterpret_cast<const float4*>(tilep + (lane + dyi) * PITCH + OX * warp);
-      float v[NV4 * 4];
-#pragma unroll
-      for (int j = 0; j < NV4; ++j) {
-        const float4 q = rp[j];
-        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-      }
-#pragma unroll
-      for (int dxi = 0; dxi < 2 * RX + 1; ++dxi) {
-        const float w = a.wbox[dyi * (2 * RX + 1) + dxi];      // constant-bank operand
-        if constexpr (SPEC != 0) {
-          if ((kBlur1Rows[SPEC - 1][dyi] >> dxi) & 1u) {
-#pragma unroll
-            for (int c = 0; c < OX; ++c) acc[c] = fmaf(w, v[c + dxi], acc[c]);
-          }
-        } else if (w != 0.f) {
-#pragma unroll
-          for (int c = 0; c < OX; ++c) acc[c] = fmaf(w, v[c + dxi], acc[c]);
-        }
-      }
-    }
-
-    // groups pending, oldest first: ops(tile), halo(tile + 1)  ->  this thread's tail operands have landed
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    const int gy = y0 + lane, gx0 = x0 + OX * warp;
-    if (gy < d.H && gx0 < d.W) {
-      const size_t g0 = (size_t)plane * d.hw + (size_t)gy * d.W + gx0;
-      const int nvalid = (d.W - gx0) < OX ? (d.W - gx0) : OX;          // a multiple of 4 (W % 4 == 0)
-#pragma unroll
-      for (int q = 0; q < OX / 4; ++q) {
-        if (4 * q >= nvalid) break;
-        if constexpr (MODE == kPrimal) {
-          const float4 xv = *reinterpret_cast<const float4*>(my_ops + 4 * q);
-          float4 r;
-          r.x = fmaf(-p.g1 * sg, acc[4 * q], xv.x); r.y = fmaf(-p.g1 * sg, acc[4 * q + 1], xv.y);
-          r.z = fmaf(-p.g1 * sg, acc[4 * q + 2], xv.z); r.w = fmaf(-p.g1 * sg, acc[4 * q + 3], xv.w);
-          *reinterpret_cast<float4*>(a.s.u + g0 + 4 * q) = r;
-        } else {
-          const float* ctr = rs + (RY + lane) * PITCH + RX + OX * warp + 4 * q;      // x+ / x at the outputs: the raw halo tiles
-          const float4 xn4 = *reinterpret_cast<const float4*>(ctr), x4 = *reinterpret_cast<const float4*>(ctr + kTile);
-          const float4 t4 = *reinterpret_cast<const float4*>(my_ops + 4 * q), ob4 = *reinterpret_cast<const float4*>(my_ops + 4096 + 4 * q);
-          float4 xt4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (have_true) xt4 = *reinterpret_cast<const float4*>(my_ops + 8192 + 4 * q);
-          const float xnv[4] = {xn4.x, xn4.y, xn4.z, xn4.w}, xv[4] = {x4.x, x4.y, x4.z, x4.w}, ob[4] = {ob4.x, ob4.y, ob4.z, ob4.w},
-                      xt[4] = {xt4.x, xt4.y, xt4.z, xt4.w};
-          float tv[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float w = fmaf(p.g2, acc[4 * q + c], sg * tv[c]);
-            if constexpr (METHOD == PDS_METHOD_C) {
-              tv[c] = gkl_dual(w, ob[c], la, lg4);
-            } else {
-              tv[c] = fmaf(-p.g2, ob[c], w);
-              acc_t = fmaf(tv[c], tv[c], acc_t);
-            }
-            const float dx = xnv[c] - xv[c];
-            acc_dx = fmaf(dx, dx, acc_dx);
-            acc_x = fmaf(xv[c], xv[c], acc_x);
-            if (have_true) {
-              const float e = xnv[c] - xt[c];
-              acc_e = fmaf(e, e, acc_e);
-            }
-          }
-          *reinterpret_cast<float4*>(a.s.t + g0 + 4 * q) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-        }
-      }
-    }
-    if (tile + 1 < t_end) issue_ops(tile + 1);               // own slots only: no barrier needed before refilling them
-    else asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (cur_b >= 0) flush_sums();
-}
-
-template <int MODE>
-constexpr size_t stream_smem_bytes() {
-  constexpr int HC = 128 + 8, HR = 32 + 16, PITCH = ((HC + 27) / 32) * 32 + 4, kTile = HR * PITCH;
-  return (size_t)(MODE == kDual ? (2 * 2 + 1) * kTile + 3 * 4096 : 2 * kTile + 4096) * sizeof(float);
-}
-
-template <int MODE, int METHOD, int SPEC>
-cudaError_t launch_stream(const BlurArgs& a0, const Dims& d, cudaStream_t st) {
-  BlurArgs a = a0;
-  a.tiles_x = (d.W + 127) / 128;
-  const int tiles_y = (d.H + 31) / 32;
-  const long long ntiles = (long long)a.tiles_x * tiles_y * d.B * d.C;
-  static PerDeviceOnce once;
-  if (once.first_use()) {
-    cudaError_t e = cudaFuncSetAttribute(blur_stream_kernel<MODE, METHOD, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)stream_smem_bytes<MODE>());
-    if (e != cudaSuccess) { once.retract(); return e; }
-  }
-  const long long slots = (long long)blur_num_sms() * (MODE == kPrimal ? 2 : 1);     // primal: two blocks fit an SM's shared memory
-  const int grid = (int)(ntiles < slots ? ntiles : slots);
-  blur_stream_kernel<MODE, METHOD, SPEC><<<grid, 256, stream_smem_bytes<MODE>(), st>>>(a, (int)ntiles, tiles_y);
-  return cudaGetLastError();
-}
-
 template <int RY, int RX, int OX>
 constexpr size_t rt_smem_bytes() {
   constexpr int HC = 8 * OX + 2 * RX, HR = 32 + 2 * RY, PITCH = ((HC + 27) / 32) * 32 + 4;
@@ -656,6 +408,16 @@ constexpr unsigned kBlur1RowsHost[2][17] = {
     {480, 480, 496, 504, 508, 510, 254, 255, 255, 255, 255, 255, 127, 127, 63, 31, 14},
     {224, 496, 504, 508, 508, 510, 510, 510, 510, 510, 254, 255, 127, 63, 31, 15, 15}};
 
+inline int blur_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    n = v;
+  }
+  return n;
+}
+
 template <int MODE, int METHOD, int RY, int RX>
 cudaError_t launch_rt(BlurArgs& a, const Dims& d, const BlurTaps& t, int which, cudaStream_t st) {
   a.tap_w = t.w[which];
@@ -679,12 +441,6 @@ cudaError_t launch_rt(BlurArgs& a, const Dims& d, const BlurTaps& t, int which, 
       match = bits == kBlur1RowsHost[which][r];
     }
     if (match) {
-      // launches that fill the GPU: the streaming kernel (persistent blocks, cp.async pipeline) when its chunked periodic wrap
-      // applies; ours-B with blur (two more tail operands) stays on the tile-per-block kernel
-      if constexpr (MODE != kApply && METHOD != PDS_METHOD_B) {
-        if (big && !t.debug_no_stream && t.debug_ox == 0 && (d.W & 3) == 0 && d.H >= RY + 32 && d.W >= RX + 128)
-          return which == 0 ? launch_stream<MODE, METHOD, 1>(a, d, st) : launch_stream<MODE, METHOD, 2>(a, d, st);
-      }
       if (big && t.debug_ox == 8)
         return which == 0 ? launch_rt_ox<MODE, METHOD, RY, RX, 8, 1>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 8, 2>(a, d, st);
       if (which == 0) return big ? launch_rt_ox<MODE, METHOD, RY, RX, 16, 1>(a, d, st) : launch_rt_ox<MODE, METHOD, RY, RX, 4, 1>(a, d, st);

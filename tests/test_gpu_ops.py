@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import rel_l2, weights_path
+from conftest import rel_l2
 from oracle import pds_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -151,36 +151,3 @@ def test_blur1_compile_time_tap_list_matches_generic_stencil(assets, shape):
         y = e.phi(xd).cpu().numpy()
     ref = np.stack([O.blur_phi(x[i].astype(np.float64), h2) for i in range(min(B, 2))])
     assert np.max(np.abs(y[: min(B, 2)] - ref.reshape(y[: min(B, 2)].shape))) < 2e-6
-
-
-@pytest.mark.parametrize("shape,method", [((12, 3, 256, 256), "A"), ((40, 1, 70, 260), "A"), ((60, 1, 96, 132), "C"), ((7, 3, 40, 1024), "A")])
-def test_streaming_stencil_matches_tile_per_block_stencil(assets, shape, method):
-    """Large launches run the fused primal / dual stencils as persistent blocks with a cp.async pipeline (blur_stream_kernel:
-    the halo of the next tile and the tail operands of the current one in flight while the FMAs run).  Same tile geometry, thread
-    mapping, FMA order and tail arithmetic as blur_rt_kernel (tc_variant bit 19 keeps large launches on it): the iterates and the
-    dual variable are bit-identical after several iterations, the trace sums agree to double round-off (block partials are added
-    in another order).  Covers tiles hanging over the right and bottom edges, rows shorter than the halo reach of a neighbour
-    (W = 132), per-block tile ranges that cross item boundaries, ours-A and ours-C."""
-    from pnp_pds_b200.engine import Engine
-    from pnp_pds_b200.models.weights import load_weights
-    B, C, H, W = shape
-    w = load_weights(weights_path("DnCNN_nobn_nch_3_nlev_0.01" if C == 3 else "DnCNN_nobn_nch_1_nlev_0.01"))
-    rng = np.random.default_rng(9)
-    x_true = rng.random(shape).astype(np.float32)
-    obs = (x_true + 0.05 * rng.standard_normal(shape)).astype(np.float32)
-    if method == "C":
-        obs = np.abs(obs) * 100.0
-    outs = []
-    for variant in (0, 524288):
-        with Engine(B, C, H, W, method=method, deg_op="blur", max_iter=4) as e:
-            e.set_blur_kernel(assets["blur_1"])
-            e.load_dncnn(w)
-            e.set_params([dict(gamma1=0.99 - 0.01 * (i % 3), gamma2=0.99, epsilon=0.5 + 0.1 * (i % 2), eta=0.0, lam=1.0, alpha=100.0) for i in range(B)])
-            e.set_tc_variant(variant)
-            e.set_problem(obs if method != "C" else obs / 100.0, obs, x_true)
-            e.run(4)
-            x, _, y = e.state(want_s=False, want_y=True)
-            outs.append((x.cpu().numpy(), y.cpu().numpy(), e.traces()))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
-    assert np.allclose(outs[0][2], outs[1][2], rtol=1e-12, atol=0)
-    assert np.isfinite(outs[0][0]).all() and outs[0][2][-1, :, 0].min() >= 0
