@@ -182,6 +182,25 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
   return r;
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rd));
+  return r;
+}
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) {
   unsigned long long ra, rb, rc;
   asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
@@ -222,16 +241,18 @@ __device__ __forceinline__ void store_half_row(__half* dst_p0, uint8_t* dst_p1, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = q * 16 + 2 * k;
+      // packed fp32 pairs (FFMA2 / FADD2 / FMUL2): the same roundings as the scalar forms in two thirds of the issue slots
       const float2 b = *reinterpret_cast<const float2*>(bias_s + c0 + c);
-      float v0 = fmaf(__uint_as_float(d1[c]), lo_scale, __uint_as_float(d0[c])) + b.x;
-      float v1 = fmaf(__uint_as_float(d1[c + 1]), lo_scale, __uint_as_float(d0[c + 1])) + b.y;
-      v0 = fmaxf(v0, v0 * slope);            // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
-      v1 = fmaxf(v1, v1 * slope);
-      const __half2 hh = __floats2half2_rn(v0, v1);
-      const float2 hf = __half22float2(hh);
+      float2 v = add2(fma2(make_float2(__uint_as_float(d1[c]), __uint_as_float(d1[c + 1])), make_float2(lo_scale, lo_scale),
+                           make_float2(__uint_as_float(d0[c]), __uint_as_float(d0[c + 1]))), b);
+      const float2 vs = mul2(v, make_float2(slope, slope));
+      v.x = fmaxf(v.x, vs.x);                // LeakyReLU for 0 <= slope <= 1 (0.01 simple_CNN, 0 KAIR ReLU)
+      v.y = fmaxf(v.y, vs.y);
+      const __half2 hh = __floats2half2_rn(v.x, v.y);
+      const float2 lo = mul2(sub2(v, __half22float2(hh)), make_float2(kActLoScale, kActLoScale));
       hi[k] = *reinterpret_cast<const uint32_t*>(&hh);
-      l[2 * k] = (v0 - hf.x) * kActLoScale;
-      l[2 * k + 1] = (v1 - hf.y) * kActLoScale;
+      l[2 * k] = lo.x;
+      l[2 * k + 1] = lo.y;
     }
     st_global_256(reinterpret_cast<uint8_t*>(dst_p0) + (size_t)(c0 / 16 + q) * cs, hi);
     if (write_a8) {                          // warp-uniform
