@@ -81,6 +81,12 @@ struct pds_handle_s {
   // pds_restore_host: x_obsrv / x_true are uploaded on a side stream while the first primal step and denoiser pass run
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_enter = nullptr, ev_inputs = nullptr;
+  // pds_restore_host, ours-A/B/C: x_0 arrives and x_{final} leaves one denoiser chunk at a time (kPipeEvents chunks at most)
+  static constexpr int kPipeEvents = 64;
+  cudaEvent_t ev_pipe[kPipeEvents] = {};       // x_0 slice of chunk c is on the device
+  cudaEvent_t ev_out = nullptr, ev_out_done = nullptr;
+  bool pipe_in = false;                       // this iteration's primal step runs per chunk, behind the chunk's upload
+  float* pipe_out_host = nullptr;             // this iteration's denoiser output is copied to the host chunk by chunk
   bool inputs_pending = false;
   size_t ev_used = 0;
   struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -219,6 +225,25 @@ BodyDispatch body_dispatch(const pds_handle_s* h, int nimg) {
   return b;
 }
 
+StepArgs step_args(pds_handle_s* h);
+// the items [b0, b0 + nimg) of a step as a step of their own (per-item rows and state slices start at item b0)
+StepArgs chunk_view(StepArgs a, int b0, int nimg) {
+  const size_t off = (size_t)b0 * a.d.n;
+  a.d.B = nimg;
+  a.x += off;
+  a.xn += off;
+  a.u += off;
+  a.t += off;
+  if (a.s_old) a.s_old += off;
+  if (a.s_new) a.s_new += off;
+  a.obs += off;
+  if (a.xtrue) a.xtrue += off;
+  a.prm += b0;
+  if (a.sums_prev) a.sums_prev += (size_t)b0 * NSUM;
+  a.sums_cur += (size_t)b0 * NSUM;
+  return a;
+}
+
 // Denoiser.denoise over all B items, `chunk` images per pass so that activations can stay in L2.
 int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
   PDS_REQUIRE(h->have_net, "denoiser weights not loaded (pds_load_dncnn)");
@@ -227,6 +252,14 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
     const int nimg = (d.B - b0 < h->chunk) ? d.B - b0 : h->chunk;
     const float* cin = in + (size_t)b0 * d.n;
     float* cout = out + (size_t)b0 * d.n;
+    if (h->pipe_in) {
+      // pds_restore_host, first iteration: the primal step of this chunk's items runs here, behind their x_0 upload, so the
+      // denoiser starts after one chunk's transfer instead of the whole batch's
+      PDS_CUDA_OK(cudaStreamWaitEvent(st, h->ev_pipe[b0 / h->chunk], 0));
+      const StepArgs ca = chunk_view(step_args(h), b0, nimg);
+      if (h->cfg.deg_op == PDS_OP_BLUR) PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_blur(ca, h->taps, st));
+      else PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_pointwise(ca, st));
+    }
     // body layers: the row-streaming kernel (dncnn_roll.cu) when the width splits into 128-pixel strips and its cost model
     // (roll_band_rows) beats the tiles; else the 2-CTA tile kernel (measured faster than the 1-CTA one at every size: half
     // the weight prologue per SM, fewer operand bytes; cfg1 264 vs 285 us per iteration, cfg2 694 vs 792).  The 1-CTA tile
@@ -270,6 +303,14 @@ int run_dncnn(pds_handle_s* h, const float* in, float* out, cudaStream_t st) {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last_tc(h->tc, src, nimg, d.C, h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
     } else {
       PDS_LAUNCH_P(h, PDS_PROF_CONV_LAST, st, launch_conv_last(nimg, d.C, d.H, d.W, h->act[src], h->layers[h->depth - 1], cin, h->res_sign, h->clamp, cout, st));
+    }
+    if (h->pipe_out_host) {
+      // pds_restore_host, last iteration: x_{k+1} of this chunk is final (the dual update only reads it) — on its way to the host
+      // while the remaining chunks are denoised
+      PDS_CUDA_OK(cudaEventRecord(h->ev_out, st));
+      PDS_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_out, 0));
+      PDS_CUDA_OK(cudaMemcpyAsync(h->pipe_out_host + (size_t)b0 * d.n, cout, (size_t)nimg * d.n * sizeof(float), cudaMemcpyDeviceToHost,
+                                  h->copy_stream));
     }
   }
   return 0;
@@ -326,7 +367,8 @@ int pds_iteration(pds_handle_s* h, cudaStream_t st) {
   StepArgs a = step_args(h);
   const bool blur = h->cfg.deg_op == PDS_OP_BLUR;
   // x_{k+1} = D(x_k - gamma1 Phi^T y_k)
-  if (blur) PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_blur(a, h->taps, st));
+  if (h->pipe_in) { /* per chunk inside run_dncnn */ }
+  else if (blur) PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_blur(a, h->taps, st));
   else PDS_LAUNCH_P(h, PDS_PROF_PRIMAL, st, launch_primal_pointwise(a, st));
   // s_{k+1} = P_l1(s_k - gamma1 y_k)
   if (h->cfg.method == PDS_METHOD_B)
@@ -646,10 +688,17 @@ int pds_create(const pds_config_t* cfg, pds_handle_t* out) {
   // side stream + events of pds_restore_host (x_obsrv / x_true upload overlapped with the first primal step)
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_enter, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_inputs, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_out_done, cudaEventDisableTiming) != cudaSuccess) {
     pds_destroy(h);
     PDS_REQUIRE(false, "could not create the copy stream / events");
   }
+  for (int i = 0; i < pds_handle_s::kPipeEvents; ++i)
+    if (cudaEventCreateWithFlags(&h->ev_pipe[i], cudaEventDisableTiming) != cudaSuccess) {
+      pds_destroy(h);
+      PDS_REQUIRE(false, "could not create the chunk events");
+    }
   *out = h;
   return 0;
 }
@@ -661,6 +710,10 @@ int pds_destroy(pds_handle_t h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->ev_enter) cudaEventDestroy(h->ev_enter);
   if (h->ev_inputs) cudaEventDestroy(h->ev_inputs);
+  if (h->ev_out) cudaEventDestroy(h->ev_out);
+  if (h->ev_out_done) cudaEventDestroy(h->ev_out_done);
+  for (cudaEvent_t e : h->ev_pipe)
+    if (e) cudaEventDestroy(e);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (void* p : h->allocs) cudaFree(p);
   delete h;
@@ -992,7 +1045,11 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
   PDS_REQUIRE(h->have_params, "pds_set_item_params has not been called");
   PDS_REQUIRE(n_iter >= 0 && h->iter + n_iter <= h->cfg.max_iter, "n_iter exceeds the max_iter the handle was created with");
   cudaStream_t st = (cudaStream_t)stream;
+  float* const host_out = h->pipe_out_host;         // set by pds_restore_host for this run only
+  const bool pipe_first = h->pipe_in;
   for (int i = 0; i < n_iter; ++i) {
+    h->pipe_in = pipe_first && i == 0;
+    h->pipe_out_host = (i == n_iter - 1) ? host_out : nullptr;
     h->ssim_now = h->ssim_mode == 1 || (h->ssim_mode == 2 && i == n_iter - 1);
     if (h->cfg.method > PDS_METHOD_C) PDS_TRY(wait_inputs(h, st));    // every other loop reads x_obsrv at its first step
     if (h->cfg.method <= PDS_METHOD_C) PDS_TRY(pds_iteration(h, st));
@@ -1004,6 +1061,8 @@ int pds_run(pds_handle_t h, int n_iter, pds_stream_t stream) {
       else PDS_TRY(admm_c_iteration(h, st));
     }
   }
+  h->pipe_in = false;
+  h->pipe_out_host = nullptr;
   return 0;
 }
 
@@ -1063,11 +1122,27 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const size_t nb = total_elems(h) * sizeof(float);
   h->cur = h->scur = h->iter = 0;
-  // x_0 on the caller's stream (the first primal step needs it); x_obsrv and x_true on a side stream, ordered after whatever
-  // the caller's stream was still doing with those buffers, and joined by the first kernel that reads them (wait_inputs)
-  PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0], x0, nb, cudaMemcpyHostToDevice, st));
-  PDS_CUDA_OK(cudaEventRecord(h->ev_enter, st));        // after x_0: it gets the whole link first
+  // ours-A/B/C with a denoiser: x_0 goes up one denoiser chunk at a time on the side stream and the first iteration's primal step
+  // and denoiser pass follow chunk by chunk (run_dncnn); in the last iteration every chunk of x_{k+1} leaves for the host as soon as
+  // its last layer is done.  Otherwise x_0 goes up on the caller's stream.  x_obsrv and x_true always follow on the side stream,
+  // ordered after whatever the caller's stream was still doing with those buffers, and are joined by the first kernel that reads
+  // them (wait_inputs).
+  const int nchunks = h->have_net && h->chunk > 0 ? (h->d.B + h->chunk - 1) / h->chunk : 0;
+  const bool pipe = h->cfg.method <= PDS_METHOD_C && h->have_net && n_iter >= 1 && nchunks >= 2 && nchunks <= pds_handle_s::kPipeEvents;
+  PDS_CUDA_OK(cudaEventRecord(h->ev_enter, st));
   PDS_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_enter, 0));
+  if (pipe) {
+    for (int c = 0; c < nchunks; ++c) {
+      const size_t b0 = (size_t)c * h->chunk, nimg = std::min((size_t)h->chunk, (size_t)h->d.B - b0);
+      PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0] + b0 * h->d.n, x0 + b0 * h->d.n, nimg * h->d.n * sizeof(float), cudaMemcpyHostToDevice,
+                                  h->copy_stream));
+      PDS_CUDA_OK(cudaEventRecord(h->ev_pipe[c], h->copy_stream));
+    }
+  } else {
+    PDS_CUDA_OK(cudaMemcpyAsync(h->xbuf[0], x0, nb, cudaMemcpyHostToDevice, st));
+    PDS_CUDA_OK(cudaEventRecord(h->ev_enter, st));        // after x_0: it gets the whole link first
+    PDS_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_enter, 0));
+  }
   PDS_CUDA_OK(cudaMemcpyAsync(h->obs, obs, nb, cudaMemcpyHostToDevice, h->copy_stream));
   h->have_true = xtrue != nullptr;
   if (xtrue) PDS_CUDA_OK(cudaMemcpyAsync(h->xtrue, xtrue, nb, cudaMemcpyHostToDevice, h->copy_stream));
@@ -1078,9 +1153,19 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
   if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
   h->have_problem = true;
-  PDS_TRY(pds_run(h, n_iter, stream));
+  h->pipe_in = pipe;
+  h->pipe_out_host = pipe ? x_out : nullptr;
+  const int rc_run = pds_run(h, n_iter, stream);
+  h->pipe_in = false;
+  h->pipe_out_host = nullptr;
+  PDS_TRY(rc_run);
   PDS_TRY(wait_inputs(h, st));              // n_iter == 0: still join the side stream before returning
-  PDS_CUDA_OK(cudaMemcpyAsync(x_out, h->xbuf[h->cur], nb, cudaMemcpyDeviceToHost, st));
+  if (pipe) {                               // the chunk copies of x_{final} on the side stream
+    PDS_CUDA_OK(cudaEventRecord(h->ev_out_done, h->copy_stream));
+    PDS_CUDA_OK(cudaStreamWaitEvent(st, h->ev_out_done, 0));
+  } else {
+    PDS_CUDA_OK(cudaMemcpyAsync(x_out, h->xbuf[h->cur], nb, cudaMemcpyDeviceToHost, st));
+  }
   if (s_out) {
     if (h->sbuf[0]) PDS_CUDA_OK(cudaMemcpyAsync(s_out, h->sbuf[h->scur], nb, cudaMemcpyDeviceToHost, st));
     else std::memset(s_out, 0, nb);

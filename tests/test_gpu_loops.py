@@ -321,3 +321,39 @@ def test_unstable_kair_loops(assets, tag):
     res2 = iteration.run_batch(g[f"{tag}/x0"][None], g[f"{tag}/obs"][None], g[f"{tag}/x_true"][None], phi, adj, prm,
                                weights_path(case["arch"]), 2, alias, case["ch"])
     assert rel_l2(res2["x"][0], g[f"{tag}/x_2"]) < REL_L2_GATE
+
+
+@pytest.mark.parametrize("method,deg_op,shape", [("A", "blur", (5, 3, 40, 48)), ("B", "random_sampling", (7, 1, 64, 64)), ("C", "blur", (4, 1, 48, 40)),
+                                                 ("A", "Id", (3, 1, 32, 36))])
+def test_restore_host_chunk_pipeline_matches_resident_run(assets, method, deg_op, shape):
+    """pds_restore_host moves x_0 up and x_final down one denoiser chunk at a time (the first iteration's primal step runs per chunk
+    behind the chunk's upload, the last iteration's denoiser output leaves chunk by chunk).  Same kernels on the same data: the
+    result is bit-identical to pds_set_problem + pds_run + pds_get_state, including a ragged last chunk, one iteration only
+    (upload and download pipelines in the same iteration), and a second call on the same handle."""
+    from pnp_pds_b200.engine import Engine
+    from pnp_pds_b200.models.weights import load_weights
+    B, C, H, W = shape
+    w = load_weights(weights_path("DnCNN_nobn_nch_3_nlev_0.01" if C == 3 else "DnCNN_nobn_nch_1_nlev_0.01"))
+    rng = np.random.default_rng(17)
+    x_true = rng.random(shape).astype(np.float32)
+    obs = (x_true + 0.05 * rng.standard_normal(shape)).astype(np.float32)
+    x0 = obs.copy()
+    if method == "C":
+        obs = np.abs(obs) * 100.0
+    prm = [dict(gamma1=0.99, gamma2=0.49 if method == "B" else 0.99, epsilon=0.4 + 0.05 * i, eta=20.0 + i, lam=1.0, alpha=100.0) for i in range(B)]
+    for n_it in (3, 1):
+        with Engine(B, C, H, W, method=method, deg_op=deg_op, max_iter=4, denoiser_chunk=2) as e:
+            if deg_op == "blur":
+                e.set_blur_kernel(assets["blur_1"])
+            if deg_op == "random_sampling":
+                e.set_mask((np.random.default_rng(3).random((H, W)) < 0.8).astype(np.uint8))
+            e.load_dncnn(w)
+            e.set_params(prm)
+            e.set_problem(x0, obs, x_true)
+            e.run(n_it)
+            xr, sr, _ = e.state(want_s=True)
+            xr, sr, tr = xr.cpu().numpy(), sr.cpu().numpy(), e.traces()
+            for rep in range(2):
+                xh, sh, th = e.restore_host(x0, obs, x_true, n_it, want_s=True)
+                assert np.array_equal(xh, xr) and np.array_equal(sh, sr), (method, n_it, rep)
+                assert np.allclose(th, tr, rtol=1e-12, atol=0)
