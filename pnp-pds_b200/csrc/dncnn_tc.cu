@@ -450,18 +450,22 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 // drain four TMEM stages.
 // ---------------------------------------------------------------------------------------------
 namespace first2 {
-constexpr int kStagesA = 4, kAcc = 4;
-constexpr int kBuilders = 4, kGrpThreads = 32, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
+constexpr int kStagesA = 3, kAcc = 4;
+// one builder warp per record stage and per window slot: a warp always returns to the same stage / slot, so it can never be two
+// barrier phases ahead of their consumers (a parity wait cannot tell phase n from phase n + 2)
+constexpr int kBuilders = 3, kGrpThreads = 32, kMmaWarp2 = 6, kEpiWarp0 = 8, kThreadsF2 = (kEpiWarp0 + 4 * kAcc) * 32;   // 768
 // Tile = 128 consecutive pixels of ONE image row (M = 128): its activations are 16 KB of consecutive addresses in plane 0 (DRAM
-// pages, full lines), and the window is 3 rows x 130 pixels = 3 x Cin TMA rows of 544 bytes.  (With 16 x 8-pixel tiles the stores
-// were 1 KB runs 128 KB apart and the kernel stopped at 4.2 TB/s; the window was 54 TMA rows of 64 bytes.)
-constexpr int kTW = 128, kWinRows = 3, kWinPitch = kTW + 2;
-constexpr int kWinPix = kWinRows * kWinPitch;                       // 390 records per tile
-constexpr int kRecPerThread = (kWinPix + 31) / 32;                  // 13
-constexpr uint32_t kChunkPlane = kWinPix * 16;                      // 6240 bytes: K-slots 0-7 (plane 0) / 8-15 (plane 1) of every record
+// pages, full lines).  Work unit = a PAIR of vertically adjacent tiles: one window of 4 rows x 130 pixels (4 x Cin TMA rows of 544
+// bytes), ONE record block, and the two tiles' MMAs read it at row offsets 0 and 1 into two TMEM stages — every hand-off of the
+// pipeline (window -> records -> MMAs -> TMEM stage -> epilogue) carries two tiles, and a third of the records are shared.
+// (With 16 x 8-pixel tiles the stores were 1 KB runs 128 KB apart and the window was 54 TMA rows of 64 bytes.)
+constexpr int kTW = 128, kPairRows = 2, kWinRows = kPairRows + 2, kWinPitch = kTW + 2;
+constexpr int kWinPix = kWinRows * kWinPitch;                       // 520 records per tile pair
+constexpr int kRecPerThread = (kWinPix + 31) / 32;                  // 17
+constexpr uint32_t kChunkPlane = kWinPix * 16;                      // 8320 bytes: K-slots 0-7 (plane 0) / 8-15 (plane 1) of every record
 constexpr uint32_t kStageBytes = 2 * kChunkPlane;
 constexpr uint32_t kWTap = 2 * 64 * 16, kWBytesF2 = 9 * kWTap;      // per tap: [chunk][oc][8 halves]
-constexpr int kStg = 4, kBoxW = kTW + 8, kBoxX = 3;                  // input-window ring.  The box starts 4 pixels left of the tile and is 136 wide:
+constexpr int kStg = 3, kBoxW = kTW + 8, kBoxX = 3;                  // input-window ring.  The box starts 4 pixels left of the tile and is 136 wide:
                                                                      // TMA wants the innermost start coordinate and extent in 16-byte multiples
                                                                      // (measured: tools/probe/tma_f32_probe.cu — x0 = 7 is an illegal instruction, 8 is fine)
 template <int CIN> struct Stg {
@@ -475,6 +479,7 @@ static_assert(kOffWst2 % 128 == 0, "staging rows are 128-byte aligned");
 static_assert(kOffStg2 % 128 == 0, "TMA destination alignment");
 constexpr uint32_t kIdescF2 = kIdescBase | ((64u >> 3) << 17);
 static_assert(kOffA2 % 16 == 0 && kStageBytes % 16 == 0 && kOffBar2 % 8 == 0, "alignment");
+static_assert(kBuilders == kStagesA && kBuilders == kStg, "one builder warp per stage and slot (barrier phases)");
 
 // K-major, no swizzle: 8 rows x 16 bytes per core matrix (rows 16 bytes apart), lbo = distance between the two K chunks of an MMA,
 // sbo = distance between 8-row groups
@@ -616,7 +621,7 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
     // ------------------------------------------------------------ record builders.  The window itself (Cin x 3 x 136 floats,
     // zero-filled outside the image = the convolution's padding) is landed by TMA, so no thread of this kernel has a global load
     // in flight when it reaches the proxy fence below (fence.proxy.async = MEMBAR + FENCE.VIEW.ASYNC: with register-prefetched
-    // loads every tile waited out a DRAM round trip there).  Four builder warps, warp g builds the tiles with it % 4 == g (13
+    // loads every tile waited out a DRAM round trip there).  Three builder warps, warp g builds the tile pairs with it % 3 == g (17
     // records per lane): a tile's build is one serial chain (wait for the window, build, wait for a free stage, store, proxy
     // fence, arrive) whose hand-offs cost more than its arithmetic — measured with the epilogue switched off: two groups of
     // three warps delivered a tile every 1 120 cycles.
@@ -682,13 +687,13 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
       mbar_arrive(bFull + 8 * stage);
     }
   } else if (warp == kMmaWarp2 + 1) {
-    // ------------------------------------------------------------ TMA producer: one (136 x 3 x Cin) box per tile
+    // ------------------------------------------------------------ TMA producer: one (136 x 4 x Cin) box per tile pair
     if (elect_one()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
         const int img = (int)fdiv((uint32_t)tile, div_img), rem = tile - img * per_img;
         const int trow = (int)fdiv((uint32_t)rem, div_tx);
-        const int y0 = trow - 1, x0 = (rem - trow * a.tiles_x) * kTW - 1 - kBoxX;
+        const int y0 = trow * kPairRows - 1, x0 = (rem - trow * a.tiles_x) * kTW - 1 - kBoxX;
         const uint32_t slot = it % kStg;
         mbar_wait(bSEmpty + 8 * slot, (uint32_t)(((it / kStg) & 1) ^ 1));
         mbar_expect_tx(bSFull + 8 * slot, Stg<CIN>::kBytes);
@@ -697,38 +702,44 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
     }
     __syncwarp();
   } else if (warp == kMmaWarp2) {
-    // ------------------------------------------------------------ MMA issuer: nine K=16 MMAs per tile, one per tap
+    // ------------------------------------------------------------ MMA issuer: nine K=16 MMAs per tile, one per tap; the two tiles
+    // of a pair read the same records one window row apart and fill the TMEM stages 2 * (it % 2) + {0, 1}
     mbar_wait(bW, 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it % kAcc, stage = it % kStagesA, use = it / kStagesA;
-      mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it / kAcc) & 1) ^ 1));
+      const uint32_t stage = it % kStagesA, use = it / kStagesA;
       mbar_wait(bFull + 8 * stage, use & 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * 64u;
       const uint32_t a0 = sA + stage * kStageBytes;
-      if (elect_one()) {
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          if ((a.dbg & 4) && t >= 3) break;              // timing probe: a third of the MMAs
-          const uint32_t shift = (uint32_t)((t / 3) * kWinPitch + (t % 3)) * 16u;
-          umma_f16(d_tmem, desc_k_none(a0 + shift, kChunkPlane, 128), desc_k_none(sW + t * kWTap, 64 * 16, 128), kIdescF2,
-                   t ? 1u : 0u);
+      for (int r = 0; r < kPairRows; ++r) {
+        const uint32_t acc = (uint32_t)(2 * (it & 1) + r);
+        mbar_wait(bTEmpty + 8 * acc, (uint32_t)(((it >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 64u;
+        if (elect_one()) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if ((a.dbg & 4) && t >= 3) break;              // timing probe: a third of the MMAs
+            const uint32_t shift = (uint32_t)((t / 3 + r) * kWinPitch + (t % 3)) * 16u;
+            umma_f16(d_tmem, desc_k_none(a0 + shift, kChunkPlane, 128), desc_k_none(sW + t * kWTap, 64 * 16, 128), kIdescF2,
+                     t ? 1u : 0u);
+          }
+          if (r == kPairRows - 1) umma_commit(bEmpty + 8 * stage);
+          umma_commit(bTFull + 8 * acc);
         }
-        umma_commit(bEmpty + 8 * stage);
-        umma_commit(bTFull + 8 * acc);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------ epilogue: four groups of four warps, group g drains the tiles
-    // with it % 4 == g = accumulator stage g
+    // ------------------------------------------------------------ epilogue: four groups of four warps, group g drains TMEM stage g
+    // = row g & 1 of the tile pairs with it % 2 == g >> 1
     const int q = warp & 3;                               // TMEM lane quadrant this warp may read
     const int grp = (warp - kEpiWarp0) >> 2;
-    int it = grp;
-    for (int tile = blockIdx.x + grp * (int)gridDim.x; tile < a.ntiles; tile += kAcc * gridDim.x, it += kAcc) {
+    const int prow = grp & 1;
+    int it = grp >> 1;
+    for (int tile = blockIdx.x + (grp >> 1) * (int)gridDim.x; tile < a.ntiles; tile += 2 * gridDim.x, it += 2) {
       const uint32_t acc = (uint32_t)grp;
-      mbar_wait(bTFull + 8 * acc, (uint32_t)((it / kAcc) & 1));
+      mbar_wait(bTFull + 8 * acc, (uint32_t)((it >> 1) & 1));
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64u;
       const uint32_t wst = base + kOffWst2 + (uint32_t)(warp - kEpiWarp0) * 8192u;
@@ -752,9 +763,10 @@ __global__ void __launch_bounds__(kThreadsF2, 1) conv_first2_kernel(const __grid
       if (!(a.dbg & 1)) {
         const int img = (int)fdiv((uint32_t)tile, div_img), rem = tile - img * per_img;
         const int trow = (int)fdiv((uint32_t)rem, div_tx);
-        const int tx0 = (rem - trow * a.tiles_x) * kTW + q * 32;          // this warp's 32 pixels of row trow
-        const int left = a.W - tx0;                                       // pixels of the piece inside the image (may be <= 0)
-        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out) + ((size_t)img * 2 * hw + (size_t)trow * a.W + tx0) * 128;
+        const int tx0 = (rem - trow * a.tiles_x) * kTW + q * 32;          // this warp's 32 pixels of image row y
+        const int y = trow * kPairRows + prow;
+        const int left = y < a.H ? a.W - tx0 : 0;                         // pixels of the piece inside the image (may be <= 0)
+        uint8_t* p0 = reinterpret_cast<uint8_t*>(a.out) + ((size_t)img * 2 * hw + (size_t)y * a.W + tx0) * 128;
         uint8_t* p1 = p0 + hw * 128;
         flush_rows<0>(wst, p0 + (lane >> 3) * 128 + (lane & 7) * 16, lane, left);
         if (a.write_a8) flush_rows<0>(wst + 4096u, p1 + (lane >> 3) * 128 + (lane & 7) * 16, lane, left);
@@ -1428,8 +1440,8 @@ cudaError_t launch_conv_first_tc(TcPlan* plan, int nimg, int C, const float* in,
   if (!im2col && (plan->W & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15u) == 0 && (C == 1 || C == 3)) {
     const CUtensorMap* m = plan_input_map(plan, in, nimg * C, C);
     a.dbg = plan->probe_bits;
-    a.tiles_x = (plan->W + first2::kTW - 1) / first2::kTW;      // strips of 128 pixels, one image row per tile
-    a.tiles_y = plan->H;
+    a.tiles_x = (plan->W + first2::kTW - 1) / first2::kTW;      // strips of 128 pixels, two image rows per work unit
+    a.tiles_y = (plan->H + first2::kPairRows - 1) / first2::kPairRows;
     a.ntiles = a.tiles_x * a.tiles_y * nimg;
     const int grid2 = a.ntiles < plan->num_sms ? a.ntiles : plan->num_sms;
     if (m == nullptr) return cudaErrorInvalidValue;
