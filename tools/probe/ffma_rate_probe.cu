@@ -17,6 +17,9 @@ __global__ void __launch_bounds__(256, 4) k(const __grid_constant__ W cw, const 
       } else if (MODE == 1) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[c] = fmaf(wr[t], v[(c + t) & 15], acc[c]);
+      } else if (MODE == 3) {          // operand pattern that cannot be paired: stays scalar FFMA
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = fmaf(cw.w[t + (c & 1)], v[(c * 7 + t) & 15], acc[c]);
       } else {
 #pragma unroll
         for (int c = 0; c < 16; c += 2) {
@@ -39,11 +42,11 @@ int main() {
   float *wg, *out; cudaMalloc(&wg, 64); cudaMemcpy(wg, cw.w, 32, cudaMemcpyHostToDevice); cudaMalloc(&out, 148 * 8 * 256 * 4);
   const int iters = 20000, grid = 148 * 4;
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
-  const char* names[3] = {"FFMA const-bank operand", "FFMA three registers", "FFMA2 (f32x2)"};
-  for (int m = 0; m < 3; ++m) {
+  const char* names[4] = {"FFMA const-bank operand", "FFMA three registers", "FFMA2 (f32x2)", "scalar FFMA (unpairable)"};
+  for (int m = 0; m < 4; ++m) {
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(a);
-      if (m == 0) k<0><<<grid, 256>>>(cw, wg, out, iters); else if (m == 1) k<1><<<grid, 256>>>(cw, wg, out, iters); else k<2><<<grid, 256>>>(cw, wg, out, iters);
+      if (m == 0) k<0><<<grid, 256>>>(cw, wg, out, iters); else if (m == 1) k<1><<<grid, 256>>>(cw, wg, out, iters); else if (m == 2) k<2><<<grid, 256>>>(cw, wg, out, iters); else k<3><<<grid, 256>>>(cw, wg, out, iters);
       cudaEventRecord(b); cudaEventSynchronize(b);
     }
     float ms; cudaEventElapsedTime(&ms, a, b);
