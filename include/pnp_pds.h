@@ -145,7 +145,8 @@ int pds_get_traces(pds_handle_t h, double* trace_host, size_t capacity_doubles, 
  * inputs (B,C,H,W) fp32 on the host; outputs x (and s, may be NULL) and the traces.  The transfers overlap the loop (pinned host
  * buffers): x_obsrv / x_true go up on a side stream under the first iteration; for ours-A/B/C with a denoiser x_0 goes up one
  * denoiser chunk at a time with the first iteration's primal step and denoiser pass following chunk by chunk, and in the last
- * iteration every chunk of x leaves for the host as soon as its last layer is done.  Returns after `stream` is synchronised. */
+ * iteration every chunk of x leaves for the host as soon as its last layer is done (page-locked x_host only; a pageable
+ * destination is filled by one copy at the end).  Returns after `stream` is synchronised. */
 int pds_restore_host(pds_handle_t h, const float* x0_host, const float* obs_host, const float* xtrue_host,
                      int n_iter, float* x_out_host, float* s_out_host, double* trace_host,
                      size_t trace_capacity_doubles, pds_stream_t stream);

@@ -1153,14 +1153,20 @@ int pds_restore_host(pds_handle_t h, const float* x0, const float* obs, const fl
   if (h->sbuf[0]) PDS_CUDA_OK(cudaMemsetAsync(h->sbuf[0], 0, nb, st));
   PDS_CUDA_OK(cudaMemsetAsync(h->sums, 0, (size_t)h->cfg.max_iter * h->d.B * NSUM * sizeof(double), st));
   h->have_problem = true;
+  // the chunk-wise download needs a page-locked destination: a copy into pageable memory blocks the host until it is done, which
+  // would stall the launches of the following chunks
+  cudaPointerAttributes pa{};
+  const bool out_pinned = cudaPointerGetAttributes(&pa, x_out) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  (void)cudaGetLastError();
+  const bool pipe_out = pipe && out_pinned;
   h->pipe_in = pipe;
-  h->pipe_out_host = pipe ? x_out : nullptr;
+  h->pipe_out_host = pipe_out ? x_out : nullptr;
   const int rc_run = pds_run(h, n_iter, stream);
   h->pipe_in = false;
   h->pipe_out_host = nullptr;
   PDS_TRY(rc_run);
   PDS_TRY(wait_inputs(h, st));              // n_iter == 0: still join the side stream before returning
-  if (pipe) {                               // the chunk copies of x_{final} on the side stream
+  if (pipe_out) {                           // the chunk copies of x_{final} on the side stream
     PDS_CUDA_OK(cudaEventRecord(h->ev_out_done, h->copy_stream));
     PDS_CUDA_OK(cudaStreamWaitEvent(st, h->ev_out_done, 0));
   } else {

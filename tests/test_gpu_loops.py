@@ -353,7 +353,13 @@ def test_restore_host_chunk_pipeline_matches_resident_run(assets, method, deg_op
             e.run(n_it)
             xr, sr, _ = e.state(want_s=True)
             xr, sr, tr = xr.cpu().numpy(), sr.cpu().numpy(), e.traces()
-            for rep in range(2):
-                xh, sh, th = e.restore_host(x0, obs, x_true, n_it, want_s=True)
+            import torch
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+            out_pinned = torch.empty(shape, dtype=torch.float32).pin_memory()
+            for rep in range(3):
+                if rep < 2:        # pageable buffers: chunk-wise upload, one download at the end
+                    xh, sh, th = e.restore_host(x0, obs, x_true, n_it, want_s=True)
+                else:              # page-locked buffers: the download is chunk-wise too
+                    xh, sh, th = e.restore_host(pin(x0), pin(obs), pin(x_true), n_it, want_s=True, out=out_pinned.numpy())
                 assert np.array_equal(xh, xr) and np.array_equal(sh, sr), (method, n_it, rep)
                 assert np.allclose(th, tr, rtol=1e-12, atol=0)
