@@ -90,6 +90,7 @@ class Engine:
         if getattr(self, "_h", None) is not None and self._h:
             self.lib.pds_destroy(self._h)
             self._h = None
+        self._staging = None
 
     def __del__(self):
         try:
@@ -236,10 +237,47 @@ class Engine:
             _lib.check(self.lib.pds_get_traces(self._h, out.ctypes.data_as(C.c_void_p), out.size, self._stream()))
         return out
 
+    # ------------------------------------------------------------------ page-locked staging of the host-buffer entry point
+    STAGING_LIMIT = 256 << 20    # bytes per array: larger batches go through the caller's (pageable) buffers
+
+    def staging(self):
+        """Five page-locked float32 buffers of the batch shape owned by this engine (x0, obs, true, x, s), or None when the batch is
+        larger than STAGING_LIMIT per array or page-locked memory cannot be had.  pds_restore_host moves page-locked buffers chunk by
+        chunk under the loop (include/pnp_pds.h); pageable ones cost a staging pass through the driver each way."""
+        if getattr(self, "_staging", None) is None:
+            self._staging = False
+            if 4 * int(np.prod(self.shape)) <= self.STAGING_LIMIT:
+                torch = _torch()
+                try:
+                    self._staging = {k: torch.empty(self.shape, dtype=torch.float32).pin_memory() for k in ("x0", "obs", "true", "x", "s")}
+                except RuntimeError:
+                    self._staging = False
+        return self._staging or None
+
+    def stage(self, name: str, src):
+        """Copy (and convert to float32, multi-threaded) an array, a tensor or a sequence of per-item arrays into the staging buffer
+        `name`; returns its numpy view."""
+        torch = _torch()
+        dst = self.staging()[name]
+
+        def tensor(a):
+            if isinstance(a, torch.Tensor):
+                return a
+            a = np.asarray(a)
+            return torch.from_numpy(a if a.flags.writeable else a.copy())      # from_numpy warns about read-only arrays (npz members)
+        if isinstance(src, (list, tuple)):
+            if len(src) != self.B:
+                raise ValueError("need one array per item")
+            for k, a in enumerate(src):
+                dst[k].copy_(tensor(a).reshape(dst[k].shape))
+        else:
+            dst.copy_(tensor(src).reshape(self.shape))
+        return dst.numpy()
+
     def restore_host(self, x0: np.ndarray, obs: np.ndarray, x_true: np.ndarray | None, n_iter: int, want_s: bool = True,
-                     out: np.ndarray | None = None):
-        """Whole job through host buffers (H2D + loop + D2H inside the C call).  `out`: optional caller-owned float32
-        buffer of the batch shape for the result (e.g. pinned memory, which the device copies into at full PCIe speed)."""
+                     out: np.ndarray | None = None, s_out: np.ndarray | None = None):
+        """Whole job through host buffers (H2D + loop + D2H inside the C call).  `out` / `s_out`: optional caller-owned float32
+        buffers of the batch shape for x and s (e.g. pinned memory, which the device copies into at full PCIe speed)."""
         f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32).reshape(self.shape)
         x0, obs, x_true = f(x0), f(obs), f(x_true)
         if out is not None:
@@ -248,7 +286,12 @@ class Engine:
             x = out.reshape(self.shape)
         else:
             x = np.empty(self.shape, dtype=np.float32)
-        s = np.empty(self.shape, dtype=np.float32) if want_s else None
+        if want_s and s_out is not None:
+            if s_out.dtype != np.float32 or not s_out.flags.c_contiguous or s_out.size != int(np.prod(self.shape)):
+                raise ValueError("s_out must be a C-contiguous float32 array of the batch shape")
+            s = s_out.reshape(self.shape)
+        else:
+            s = np.empty(self.shape, dtype=np.float32) if want_s else None
         tr = np.zeros((int(n_iter), self.B, TRACE_WIDTH), dtype=np.float64)
         hp = lambda a: C.c_void_p(0) if a is None else a.ctypes.data_as(C.c_void_p)
         _lib.check(self.lib.pds_restore_host(self._h, hp(x0), hp(obs), hp(x_true), int(n_iter), hp(x), hp(s), hp(tr), tr.size,

@@ -130,10 +130,16 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         raise ValueError(f"Unknown method: {method}")
     mid = RESIDENT_METHODS[name]
     kind = _check_ops(phi, adj_phi)
-    x_0 = np.asarray(x_0)
-    B = x_0.shape[0]
-    H, W = x_0.shape[-2:]
-    C = 1 if x_0.ndim == 3 else x_0.shape[1]
+    # x_0 / x_obsrv / x_true: one array (B, ...) or a sequence of B per-item arrays (converted straight into the engine's page-locked
+    # staging buffers, without stacking them first)
+    as_items = isinstance(x_0, (list, tuple))
+    if not as_items:
+        x_0 = np.asarray(x_0)
+    B = len(x_0)
+    item_shape = tuple(np.shape(x_0[0]))
+    H, W = item_shape[-2:]
+    C = 1 if len(item_shape) == 2 else item_shape[0]
+    batch_shape = (B,) + item_shape
     if C != ch:
         raise ValueError(f"ch={ch} but the images have {C} channels")
     n = C * H * W
@@ -162,7 +168,15 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         import torch
         launches0 = eng.kernel_launches
         t0 = time.perf_counter()
-        x, s, tr = eng.restore_host(x_0, x_obsrv, x_true, int(max_iter), want_s=True)
+        if eng.staging() is not None:
+            hx0, hobs = eng.stage("x0", x_0), eng.stage("obs", x_obsrv)
+            htrue = None if x_true is None else eng.stage("true", x_true)
+            st = eng.staging()
+            x, s, tr = eng.restore_host(hx0, hobs, htrue, int(max_iter), want_s=True, out=st["x"].numpy(), s_out=st["s"].numpy())
+            x, s = x.copy(), s.copy()                                  # the staging buffers belong to the (cached) engine
+        else:
+            stack = lambda a: None if a is None else (np.stack([np.asarray(v) for v in a]) if isinstance(a, (list, tuple)) else a)
+            x, s, tr = eng.restore_host(stack(x_0), stack(x_obsrv), stack(x_true), int(max_iter), want_s=True)
         torch.cuda.synchronize(eng.device)
         wall = time.perf_counter() - t0
         launches = eng.kernel_launches - launches0
@@ -171,8 +185,8 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         raise
     _release_engine(key, eng)
     c, psnr = metrics_from_traces(tr, n)                              # [it, B]
-    x = x.reshape(x_0.shape)
-    s = s.reshape(x_0.shape)
+    x = x.reshape(batch_shape)
+    s = s.reshape(batch_shape)
     ssim_data = ssim_from_traces(tr, C, H, W)                          # [it, B]; evaluated on the device
     return dict(x=x, s=s, c=c, psnr=psnr, ssim=ssim_data, time_per_iter=wall / max(1, int(max_iter)), traces=tr,
                 launches=launches)

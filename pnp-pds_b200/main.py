@@ -179,7 +179,7 @@ def grid_search(images, grid, experimental_settings, method_common, ch, path_ker
             prms.append(dict(gamma1=base["gamma1"], gamma2=base["gamma2"], alpha_s=base["alpha_s"], alpha_n=base["alpha_n"],
                              myLambda=base["myLambda"], gaussian_nl=gaussian_nl, sp_nl=sp_nl, poisson_alpha=poisson_alpha, r=r))
         t0 = time.perf_counter()
-        res = iteration.run_batch(np.stack(x0s), np.stack(obss), np.stack(trues), phi, adj_phi, prms, path_prox, max_iter, method,
+        res = iteration.run_batch(x0s, obss, trues, phi, adj_phi, prms, path_prox, max_iter, method,   # per-item arrays: no stacking pass
                                   ch, conv_engine=conv_engine, device=local_rank if world > 1 else None)
         t_run += time.perf_counter() - t0
         for k, it in enumerate(ids):
