@@ -249,7 +249,7 @@ class Engine:
             if 4 * int(np.prod(self.shape)) <= self.STAGING_LIMIT:
                 torch = _torch()
                 try:
-                    self._staging = {k: torch.empty(self.shape, dtype=torch.float32).pin_memory() for k in ("x0", "obs", "true", "x", "s")}
+                    self._staging = {k: torch.empty(self.shape, dtype=torch.float32, pin_memory=True) for k in ("x0", "obs", "true", "x", "s")}
                 except RuntimeError:
                     self._staging = False
         return self._staging or None
@@ -268,8 +268,16 @@ class Engine:
         if isinstance(src, (list, tuple)):
             if len(src) != self.B:
                 raise ValueError("need one array per item")
-            for k, a in enumerate(src):
-                dst[k].copy_(tensor(a).reshape(dst[k].shape))
+            put = lambda k: dst[k].copy_(tensor(src[k]).reshape(dst[k].shape))
+            if self.B >= 32:
+                # a few host threads: under torchrun every rank runs with OMP_NUM_THREADS=1, and the float64 -> float32 conversion
+                # of a batch is then the longest host-side step of a short job (copy_ releases the GIL)
+                from concurrent.futures import ThreadPoolExecutor
+                with ThreadPoolExecutor(max_workers=4) as pool:
+                    list(pool.map(put, range(self.B)))
+            else:
+                for k in range(self.B):
+                    put(k)
         else:
             dst.copy_(tensor(src).reshape(self.shape))
         return dst.numpy()

@@ -93,7 +93,12 @@ def _acquire_engine(B, C, H, W, mid, kind, phi, max_iter, conv_engine, device, d
         eng.close()
         eng = None
     if eng is None:
-        eng = Engine(B, C, H, W, method=mid, deg_op=kind, max_iter=max(1, int(max_iter)), conv_engine=conv_engine, device=device,
+        # trace capacity in powers of two from 32: a short warm-up call followed by the real one (or a sweep over iteration counts)
+        # reuses the handle instead of rebuilding it (workspace, weights, page-locked staging) inside the second call
+        cap = 32
+        while cap < max_iter:
+            cap *= 2
+        eng = Engine(B, C, H, W, method=mid, deg_op=kind, max_iter=cap, conv_engine=conv_engine, device=device,
                      denoiser_chunk=denoiser_chunk)
         try:
             if kind == "blur":
@@ -168,15 +173,19 @@ def run_batch(x_0, x_obsrv, x_true, phi, adj_phi, params: Sequence[dict] | dict,
         import torch
         launches0 = eng.kernel_launches
         t0 = time.perf_counter()
+        sparse = mid in ("B", "ADMM_B2", "TV_B3")                     # the methods that carry s; for the others s == 0 (iteration.py:24)
         if eng.staging() is not None:
             hx0, hobs = eng.stage("x0", x_0), eng.stage("obs", x_obsrv)
             htrue = None if x_true is None else eng.stage("true", x_true)
             st = eng.staging()
-            x, s, tr = eng.restore_host(hx0, hobs, htrue, int(max_iter), want_s=True, out=st["x"].numpy(), s_out=st["s"].numpy())
-            x, s = x.copy(), s.copy()                                  # the staging buffers belong to the (cached) engine
+            x, s, tr = eng.restore_host(hx0, hobs, htrue, int(max_iter), want_s=sparse, out=st["x"].numpy(), s_out=st["s"].numpy())
+            x = x.copy()                                               # the staging buffers belong to the (cached) engine
+            s = s.copy() if sparse else None
         else:
             stack = lambda a: None if a is None else (np.stack([np.asarray(v) for v in a]) if isinstance(a, (list, tuple)) else a)
-            x, s, tr = eng.restore_host(stack(x_0), stack(x_obsrv), stack(x_true), int(max_iter), want_s=True)
+            x, s, tr = eng.restore_host(stack(x_0), stack(x_obsrv), stack(x_true), int(max_iter), want_s=sparse)
+        if s is None:
+            s = np.zeros(batch_shape, dtype=np.float32)
         torch.cuda.synchronize(eng.device)
         wall = time.perf_counter() - t0
         launches = eng.kernel_launches - launches0
