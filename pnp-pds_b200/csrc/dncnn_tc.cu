@@ -435,19 +435,19 @@ __global__ void __launch_bounds__(kThreadsF, 1) conv_first_tc_kernel(FirstArgs a
 }  // namespace first
 
 // ---------------------------------------------------------------------------------------------
-// First layer, tap-shifted form (the default; conv_first_tc_kernel above is kept as the cross-check, tc_variant bit 15).
-// The im2col kernel above spends half of its issue slots building the 128 x 27 patch matrix (ncu: producers 47 % of the
-// stall samples, epilogue 48 %).  Here nothing is gathered: every halo pixel of the 18 x 10 window is ONE 32-byte record of 16
-// fp16 K-slots
+// First layer, tap-shifted form (the default; conv_first_tc_kernel above is kept as the cross-check, tc_variant bit 15, and serves
+// widths with W % 4 != 0).  The im2col kernel above spends half of its issue slots building the 128 x 27 patch matrix (ncu:
+// producers 47 % of the stall samples, epilogue 48 %).  Here nothing is gathered: every pixel of the input window (4 rows x 130
+// pixels for a pair of 128-pixel tiles, see below) is ONE 32-byte record of 16 fp16 K-slots
 //     [ a_hi(c) | a_lo(c) | a_hi(c) | 1 1 1 | 0 .. ]        c = 0..Cin-1,  a = a_hi + a_lo
 // stored as two un-swizzled K-major planes (slots 0-7 / 8-15, 16 bytes per pixel each), and tap (dy,dx) is the same window read
-// through a descriptor whose start address is shifted by (dy*10 + dx) * 16 bytes (8-row groups 160 bytes apart = one window
-// row) — the trick of the body layers at K = 16 instead of 64.  The B rows of tap t hold
+// through a descriptor whose start address is shifted by (dy*130 + dx) * 16 bytes (8-row groups = 8 consecutive pixels, 128 bytes
+// apart) — the trick of the body layers at K = 16 instead of 64.  The B rows of tap t hold
 //     [ w_hi(c) | w_hi(c) | w_lo(c) | bias as three fp16 terms (centre tap only) | 0 .. ]
 // so one M=128, N=64, K=16 MMA per tap accumulates a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ bias): 9 MMAs per tile into ONE fp32
-// accumulator, no correction accumulator, no bias add in the epilogue.  The fp32 window is landed by TMA (one 16 x 18 x Cin box
-// per tile); two groups of three builder warps turn it into the 180 records of a tile; sixteen epilogue warps in four groups
-// drain four TMEM stages.
+// accumulator, no correction accumulator, no bias add in the epilogue.  The fp32 window is landed by TMA (one 136 x 4 x Cin box
+// per tile pair); three builder warps turn it into the 520 records of a pair; sixteen epilogue warps in four groups drain four
+// TMEM stages and store whole 128-byte lines through per-warp staging rows.
 // ---------------------------------------------------------------------------------------------
 namespace first2 {
 constexpr int kStagesA = 3, kAcc = 4;
